@@ -1,0 +1,51 @@
+"""CPU: host-side adaptor logic that needs no device (counts, unfused Decimate, sharding maths)."""
+import numpy as np
+
+import gen
+import oracle_lib as O
+
+
+def test_unfused_decimate_take_skip_block(sdr):
+    S = sdr.signal
+    ramp = np.arange(1000, dtype=np.float32)
+    s = S.from_array(2.4e6, ramp).decimate(240e3)
+    assert s.wait == 10 and not s.fused and s.rate() == np.float32(2.4e6)  # rate() quirk, adapters/mod.rs:38-40
+    assert np.array_equal(s.collect(block=37), O.decimate(ramp, 10)[0])
+    t = S.from_array(1000.0, ramp).skip(0.1).take(0.25)
+    assert np.array_equal(t.collect(block=64), ramp[100:350])
+    b = S.from_array(1000.0, ramp).block(0.0305)
+    assert b.block_size == O.block_size(0.0305, 1000.0) == 31
+    assert len(b.next_block(1 << 20)) == 31
+    m = S.from_array(1000.0, ramp).map(lambda v: v * 2)
+    assert np.array_equal(m.collect(), ramp * 2)
+
+
+def test_shard_ranges_cover_and_align(sdr):
+    sh = sdr.shard
+    for n, w, D, K in [(2 ** 20, 8, 1, 64), (24_000_007, 8, 10, 255), (1000, 3, 7, 5), (10, 4, 1, 3)]:
+        prev_hi = 0
+        outs = 0
+        for r in range(w):
+            lo, hi, hlo = sh.sample_range(n, w, r, K - 1, D)
+            assert lo == prev_hi and lo % D == 0 and hlo == max(0, lo - (K - 1))
+            olo, ohi = sh.output_range(n, w, r, D)
+            assert olo == outs
+            outs = ohi
+            prev_hi = hi
+        assert prev_hi == n and outs == n // D
+    assert [sh.unit_range(10, 4, r) for r in range(4)] == [(0, 2), (2, 5), (5, 7), (7, 10)]
+
+
+def test_sharded_fir_equals_single_stream_on_oracle(sdr):
+    """the partitioning itself (cut on multiples of D, K-1 halo) preserves every output sample"""
+    iq = gen.fm_u8(30011, 2.4e6, 75e3, 1e3, 0.05, 5)
+    taps = gen.lowpass_taps(255, 100e3, 2.4e6)
+    x = O.unpack_u8iq(iq)
+    whole = O.Fir(taps).apply(x)[9::10]
+    parts = []
+    for r in range(4):
+        lo, hi, hlo = sdr.shard.sample_range(len(x), 4, r, 254, 10)
+        f = O.Fir(taps)
+        f.apply(x[hlo:lo])  # prime with the halo
+        parts.append(f.apply(x[lo:hi])[9::10])
+    assert np.array_equal(np.concatenate(parts), whole)

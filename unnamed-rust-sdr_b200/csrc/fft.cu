@@ -1,0 +1,414 @@
+// fft.cu -- K3: batched forward FFT, fused input unpack and fftshift + 1/sqrt(N) on store.
+//
+// Replaces rustfft's FFTplanner::plan_fft + process as called by fft::fft (src/fft.rs:10-12) and
+// the shift/normalise loop of src/fft.rs:14-26 (and rfft's drain, src/fft.rs:34-36).
+//
+// Algorithm: Stockham autosort, decimation in time, radix-16 passes held in registers (a final
+// radix 2/4/8 pass when log2 N is not a multiple of 4).  Every thread owns 16 points; pass data is
+// exchanged through padded shared memory (index a -> a + a/16, which makes both the stride-16
+// scatter of the first pass and the unit-stride gathers of later passes bank-conflict free).
+// Twiddles come from a table computed on the host in f64 and rounded to f32 (as rustfft does).
+//
+//   n = 16 .. 16384    one kernel; a CTA holds whole transforms in shared memory (one HBM pass)
+//   n = 32768, 65536   two kernels (four-step): 256-point column FFTs, then (n/256)-point column
+//                      FFTs with the W_n^{k r} twiddle folded into the load.  The intermediate is
+//                      written in place in the output buffer.
+#include "kernels.h"
+
+namespace sdr {
+
+namespace {
+
+constexpr float C_SQRT1_2 = 0.70710678118654752440f;
+constexpr float C_COS_PI_8 = 0.92387953251128675613f;
+constexpr float C_SIN_PI_8 = 0.38268343236508977173f;
+
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
+
+// forward 4-point DFT in place on a, b, c, d -> X0..X3
+__device__ __forceinline__ void dft4(float2 &a, float2 &b, float2 &c, float2 &d) {
+    const float2 s02 = cadd(a, c), d02 = csub(a, c), s13 = cadd(b, d), d13 = mul_mi(csub(b, d));
+    a = cadd(s02, s13);
+    b = cadd(d02, d13);
+    c = csub(s02, s13);
+    d = csub(d02, d13);
+}
+
+// R-point forward DFT over v[0], v[S], ..., v[(R-1)S]; natural order in and out.
+template <int R, int S>
+__device__ __forceinline__ void dft(float2 *v) {
+    if (R == 2) {
+        const float2 a = v[0], b = v[S];
+        v[0] = cadd(a, b);
+        v[S] = csub(a, b);
+    } else if (R == 4) {
+        dft4(v[0], v[S], v[2 * S], v[3 * S]);
+    } else if (R == 8) {
+        // n = c + 2a: U[c][r] = DFT4_a(v[c+2a]); X[r] = U0[r] + W8^r U1[r]; X[r+4] = U0[r] - W8^r U1[r]
+        float2 e0 = v[0], e1 = v[2 * S], e2 = v[4 * S], e3 = v[6 * S];
+        float2 o0 = v[S], o1 = v[3 * S], o2 = v[5 * S], o3 = v[7 * S];
+        dft4(e0, e1, e2, e3);
+        dft4(o0, o1, o2, o3);
+        o1 = make_float2((o1.x + o1.y) * C_SQRT1_2, (o1.y - o1.x) * C_SQRT1_2);   // * W8^1 = (1-i)/sqrt2
+        o2 = mul_mi(o2);                                                          // * W8^2 = -i
+        o3 = make_float2((o3.y - o3.x) * C_SQRT1_2, -(o3.x + o3.y) * C_SQRT1_2);  // * W8^3 = (-1-i)/sqrt2
+        v[0] = cadd(e0, o0); v[4 * S] = csub(e0, o0);
+        v[S] = cadd(e1, o1); v[5 * S] = csub(e1, o1);
+        v[2 * S] = cadd(e2, o2); v[6 * S] = csub(e2, o2);
+        v[3 * S] = cadd(e3, o3); v[7 * S] = csub(e3, o3);
+    } else {  // R == 16, S == 1
+        // n = c + 4a: U[c][r] = DFT4_a(v[c+4a]); X[r+4q] = DFT4_c(W16^{c r} U[c][r])[q]
+        float2 u[4][4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            u[c][0] = v[c * S]; u[c][1] = v[(c + 4) * S]; u[c][2] = v[(c + 8) * S]; u[c][3] = v[(c + 12) * S];
+            dft4(u[c][0], u[c][1], u[c][2], u[c][3]);
+        }
+        const float2 w1 = make_float2(C_COS_PI_8, -C_SIN_PI_8);
+        const float2 w2 = make_float2(C_SQRT1_2, -C_SQRT1_2);
+        const float2 w3 = make_float2(C_SIN_PI_8, -C_COS_PI_8);
+        const float2 w6 = make_float2(-C_SQRT1_2, -C_SQRT1_2);
+        const float2 w9 = make_float2(-C_COS_PI_8, C_SIN_PI_8);
+        u[1][1] = cmul(u[1][1], w1); u[1][2] = cmul(u[1][2], w2); u[1][3] = cmul(u[1][3], w3);
+        u[2][1] = cmul(u[2][1], w2); u[2][2] = mul_mi(u[2][2]);   u[2][3] = cmul(u[2][3], w6);
+        u[3][1] = cmul(u[3][1], w3); u[3][2] = cmul(u[3][2], w6); u[3][3] = cmul(u[3][3], w9);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            dft4(u[0][r], u[1][r], u[2][r], u[3][r]);
+            v[r * S] = u[0][r]; v[(r + 4) * S] = u[1][r]; v[(r + 8) * S] = u[2][r]; v[(r + 12) * S] = u[3][r];
+        }
+    }
+}
+
+__device__ __forceinline__ int pad(int a) { return a + (a >> 4); }
+__host__ __device__ constexpr int padlen(int n) { return n + (n >> 4) + 1; }
+
+// One Stockham pass over a length-L sequence resident in shared memory.  TC = L/16 threads
+// cooperate; thread t owns butterflies i = t + vi*TC (vi < 16/R), whose s-th input is element
+// t + (vi + s*(16/R))*TC -- i.e. register e always maps to element t + e*TC.
+template <int LOGL, int R, int PLOG>
+__device__ __forceinline__ void fft_pass(float2 *s, int t, const float2 *__restrict__ tw, int tw_stride) {
+    constexpr int L = 1 << LOGL, TC = L / 16, NB = 16 / R, p = 1 << PLOG;
+    float2 v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = s[pad(t + e * TC)];
+    if (PLOG > 0) {
+        constexpr int tstep = L / (p * R);
+#pragma unroll
+        for (int vi = 0; vi < NB; ++vi) {
+            const int k = (t + vi * TC) & (p - 1);
+#pragma unroll
+            for (int q = 1; q < R; ++q) {
+                const float2 w = __ldg(tw + (long long)(q * k * tstep) * tw_stride);
+                v[vi + q * NB] = cmul(v[vi + q * NB], w);
+            }
+        }
+    }
+#pragma unroll
+    for (int vi = 0; vi < NB; ++vi) dft<R, NB>(v + vi);
+    __syncthreads();
+#pragma unroll
+    for (int vi = 0; vi < NB; ++vi) {
+        const int i = t + vi * TC;
+        const int k = i & (p - 1);
+        const int base = (i - k) * R + k;
+#pragma unroll
+        for (int q = 0; q < R; ++q) s[pad(base + q * p)] = v[vi + q * NB];
+    }
+    __syncthreads();
+}
+
+// all passes: radix 16 while 4 bits remain, then one pass of radix 2^(LOGL % 4)
+template <int LOGL, int PLOG>
+__device__ __forceinline__ void fft_core(float2 *s, int t, const float2 *__restrict__ tw, int tw_stride) {
+    if constexpr (PLOG < LOGL) {
+        constexpr int rem = LOGL - PLOG;
+        constexpr int RL = rem >= 4 ? 4 : rem;
+        fft_pass<LOGL, (1 << RL), PLOG>(s, t, tw, tw_stride);
+        fft_core<LOGL, PLOG + RL>(s, t, tw, tw_stride);
+    }
+}
+
+template <int FMT>
+__device__ __forceinline__ float2 load_elem(const void *in, long long idx) {
+    if (FMT == SDR_FMT_U8IQ) return unpack_iq_u16(__ldg(reinterpret_cast<const uint16_t *>(in) + idx));
+    if (FMT == SDR_FMT_C64) return __ldg(reinterpret_cast<const float2 *>(in) + idx);
+    return make_float2(__ldg(reinterpret_cast<const float *>(in) + idx), 0.0f);
+}
+
+// where spectrum bin k lands in the output row, or -1 if dropped (rfft)
+__device__ __forceinline__ int out_slot(int k, int n, unsigned flags) {
+    if (flags & SDR_FFT_RFFT) return (k < n - n / 2) ? k : -1;
+    if (flags & SDR_FFT_SHIFT) return (k + n / 2) & (n - 1);
+    return k;
+}
+
+// ---- n <= 16384: whole transforms per CTA ------------------------------------------------
+template <int LOGN, int FMT>
+__global__ void __launch_bounds__((1 << LOGN) / 16 > 256 ? (1 << LOGN) / 16 : 256)
+fft_cta_kernel(FftArgs a) {
+    constexpr int N = 1 << LOGN, TC = N / 16;
+    constexpr int THREADS = TC > 256 ? TC : 256;
+    constexpr int SEQ = THREADS / TC;
+    constexpr int SSTRIDE = padlen(N);
+    extern __shared__ float4 smem4[];
+    float2 *sm = reinterpret_cast<float2 *>(smem4);
+    const int tid = threadIdx.x;
+    const long long seq0 = (long long)blockIdx.x * SEQ;
+    const int nseq = (int)min((long long)SEQ, a.batches - seq0);
+    const int out_len = (a.flags & SDR_FFT_RFFT) ? N - N / 2 : N;
+
+    for (int idx = tid; idx < SEQ * N; idx += THREADS) {
+        const int q = idx >> LOGN, j = idx & (N - 1);
+        float2 v = make_float2(0.0f, 0.0f);
+        if (q < nseq) v = load_elem<FMT>(a.in, (seq0 + q) * N + j);
+        sm[q * SSTRIDE + pad(j)] = v;
+    }
+    __syncthreads();
+    fft_core<LOGN, 0>(sm + (tid / TC) * SSTRIDE, tid % TC, a.tw, 1);
+    const bool norm = (a.flags & SDR_FFT_NORM) != 0;
+    for (int idx = tid; idx < SEQ * N; idx += THREADS) {
+        const int q = idx >> LOGN, j = idx & (N - 1);  // j = output slot
+        if (q >= nseq || j >= out_len) continue;
+        int k = j;
+        if (!(a.flags & SDR_FFT_RFFT) && (a.flags & SDR_FFT_SHIFT)) k = (j + N / 2) & (N - 1);  // src bin
+        float2 v = sm[q * SSTRIDE + pad(k)];
+        if (norm) { v.x *= a.norm; v.y *= a.norm; }
+        a.out[(seq0 + q) * out_len + j] = v;
+    }
+}
+
+// ---- n = 2^15, 2^16: four-step, tile of 16 columns per CTA --------------------------------
+// STEP 0: view x as [256][M] (M = n/256); 256-point FFT down each column c; result row-major
+//         scratch[256*c + k2] (in the output buffer).
+// STEP 1: view scratch as [M][256]; element r of column k is scratch[k + 256 r] * W_n^{k r};
+//         M-point FFT down the column; bin k1 is X[k + 256 k1].
+template <int LOGL, int FMT, int STEP>
+__global__ void __launch_bounds__(16 * ((1 << LOGL) / 16)) fft_cols_kernel(FftArgs a) {
+    constexpr int L = 1 << LOGL, TC = L / 16, THREADS = 16 * TC;
+    constexpr int SSTRIDE = padlen(L);  // odd multiple-of-2 offset keeps the 16 columns on distinct banks
+    extern __shared__ float4 smem4[];
+    float2 *sm = reinterpret_cast<float2 *>(smem4);
+    const int tid = threadIdx.x;
+    const int n = 1 << a.log_n;
+    const int M = n >> 8;
+    const int ncol_tiles = (STEP == 0 ? M : 256) / 16;
+    const long long b = blockIdx.x / ncol_tiles;
+    const int col0 = (blockIdx.x % ncol_tiles) * 16;
+    const int cstride = (STEP == 0) ? M : 256;  // distance between consecutive rows of a column
+    const int c = tid & 15;
+    float2 *xb = a.out + b * n;  // scratch / output row of this transform (n complex)
+    for (int r = tid >> 4; r < L; r += THREADS / 16) {
+        float2 v;
+        if (STEP == 0) {
+            v = load_elem<FMT>(a.in, b * n + (long long)(col0 + c) + (long long)cstride * r);
+        } else {
+            v = xb[(col0 + c) + cstride * r];
+            v = cmul(v, __ldg(a.tw + (long long)(col0 + c) * r));
+        }
+        sm[c * SSTRIDE + pad(r)] = v;
+    }
+    __syncthreads();
+    fft_core<LOGL, 0>(sm + (tid / TC) * SSTRIDE, tid % TC, a.tw, n >> LOGL);
+    if (STEP == 0) {
+        for (int idx = tid; idx < 16 * L; idx += THREADS) {
+            const int cc = idx >> LOGL, k = idx & (L - 1);
+            xb[(long long)(col0 + cc) * L + k] = sm[cc * SSTRIDE + pad(k)];
+        }
+    } else {
+        const bool norm = (a.flags & SDR_FFT_NORM) != 0;
+        const int out_len = (a.flags & SDR_FFT_RFFT) ? n - n / 2 : n;
+        float2 *ob = a.out + b * out_len;
+        for (int r = tid >> 4; r < L; r += THREADS / 16) {
+            const int k = (col0 + c) + 256 * r;  // spectrum bin
+            const int slot = out_slot(k, n, a.flags);
+            if (slot < 0) continue;
+            float2 v = sm[c * SSTRIDE + pad(r)];
+            if (norm) { v.x *= a.norm; v.y *= a.norm; }
+            ob[slot] = v;
+        }
+    }
+}
+
+// ---- tiny sizes: direct DFT, one thread per output bin ---------------------------------------
+template <int FMT>
+__global__ void fft_naive_kernel(const void *in, float2 *out, const float2 *__restrict__ tw, long long batches,
+                                 int n, unsigned flags, float norm) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int out_len = (flags & SDR_FFT_RFFT) ? n - n / 2 : n;
+    if (gid >= batches * out_len) return;
+    const long long b = gid / out_len;
+    const int j = (int)(gid % out_len);
+    int k = j;
+    if (!(flags & SDR_FFT_RFFT) && (flags & SDR_FFT_SHIFT)) {
+        k = j - n / 2;
+        if (k < 0) k += n;
+    }
+    float2 acc = make_float2(0.0f, 0.0f);
+    int ph = 0;
+    for (int i = 0; i < n; ++i) {
+        const float2 x = load_elem<FMT>(in, b * n + i);
+        acc = cadd(acc, cmul(x, __ldg(tw + ph)));
+        ph += k;
+        if (ph >= n) ph -= n;
+    }
+    if (flags & SDR_FFT_NORM) { acc.x *= norm; acc.y *= norm; }
+    out[gid] = acc;
+}
+
+template <int LOGN, int FMT>
+int launch_cta(const FftArgs &a, cudaStream_t st) {
+    constexpr int N = 1 << LOGN, TC = N / 16;
+    constexpr int THREADS = TC > 256 ? TC : 256;
+    constexpr int SEQ = THREADS / TC;
+    const size_t smem = (size_t)SEQ * padlen(N) * sizeof(float2);
+    auto kern = fft_cta_kernel<LOGN, FMT>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e);
+    }
+    const long long ctas = (a.batches + SEQ - 1) / SEQ;
+    kern<<<(unsigned)ctas, THREADS, smem, st>>>(a);
+    count_launch();
+    return launch_status();
+}
+
+template <int FMT>
+int launch_big(const FftArgs &a, cudaStream_t st) {
+    const int n = 1 << a.log_n, M = n >> 8;
+    if ((a.flags & SDR_FFT_RFFT) != 0) return SDR_ERR_UNSUPPORTED;  // in-place scratch needs n outputs per row
+    {
+        const size_t smem = (size_t)16 * padlen(256) * sizeof(float2);
+        const long long ctas = a.batches * (M / 16);
+        fft_cols_kernel<8, FMT, 0><<<(unsigned)ctas, 256, smem, st>>>(a);
+        count_launch();
+        int rc = launch_status();
+        if (rc) return rc;
+    }
+    const long long ctas = a.batches * 16;
+    if (M == 128) {
+        const size_t smem = (size_t)16 * padlen(128) * sizeof(float2);
+        fft_cols_kernel<7, FMT, 1><<<(unsigned)ctas, 128, smem, st>>>(a);
+    } else {
+        const size_t smem = (size_t)16 * padlen(256) * sizeof(float2);
+        fft_cols_kernel<8, FMT, 1><<<(unsigned)ctas, 256, smem, st>>>(a);
+    }
+    count_launch();
+    return launch_status();
+}
+
+template <int FMT>
+int launch_fmt(const FftArgs &a, cudaStream_t st) {
+    switch (a.log_n) {
+        case 4: return launch_cta<4, FMT>(a, st);
+        case 5: return launch_cta<5, FMT>(a, st);
+        case 6: return launch_cta<6, FMT>(a, st);
+        case 7: return launch_cta<7, FMT>(a, st);
+        case 8: return launch_cta<8, FMT>(a, st);
+        case 9: return launch_cta<9, FMT>(a, st);
+        case 10: return launch_cta<10, FMT>(a, st);
+        case 11: return launch_cta<11, FMT>(a, st);
+        case 12: return launch_cta<12, FMT>(a, st);
+        case 13: return launch_cta<13, FMT>(a, st);
+        case 14: return launch_cta<14, FMT>(a, st);
+        case 15:
+        case 16: return launch_big<FMT>(a, st);
+    }
+    return SDR_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+
+int fft_pow2_launch(const FftArgs &a, cudaStream_t st) {
+    if (a.batches <= 0) return SDR_OK;
+    if (a.batches > 0x7fffffffLL) return SDR_ERR_INVALID_ARG;
+    switch (a.fmt) {
+        case SDR_FMT_U8IQ: return launch_fmt<SDR_FMT_U8IQ>(a, st);
+        case SDR_FMT_C64: return launch_fmt<SDR_FMT_C64>(a, st);
+        case SDR_FMT_F32: return launch_fmt<SDR_FMT_F32>(a, st);
+    }
+    return SDR_ERR_INVALID_ARG;
+}
+
+int fft_naive_launch(const void *in, float2 *out, const float2 *tw, long long batches, int n, int fmt,
+                     unsigned flags, float norm, cudaStream_t st) {
+    if (batches <= 0 || n <= 0) return SDR_OK;
+    const int out_len = (flags & SDR_FFT_RFFT) ? n - n / 2 : n;
+    const long long total = batches * out_len;
+    const unsigned grid = (unsigned)((total + 127) / 128);
+    if (fmt == SDR_FMT_U8IQ)
+        fft_naive_kernel<SDR_FMT_U8IQ><<<grid, 128, 0, st>>>(in, out, tw, batches, n, flags, norm);
+    else if (fmt == SDR_FMT_C64)
+        fft_naive_kernel<SDR_FMT_C64><<<grid, 128, 0, st>>>(in, out, tw, batches, n, flags, norm);
+    else
+        fft_naive_kernel<SDR_FMT_F32><<<grid, 128, 0, st>>>(in, out, tw, batches, n, flags, norm);
+    count_launch();
+    return launch_status();
+}
+
+// ---- Bluestein (chirp-z) stages for arbitrary n: X[k] = conj(w[k]) * sum_j (x[j] conj(w[j])) w[k-j],
+// w[j] = e^{+i pi j^2 / n}.  chirp[j] holds conj(w[j]) = e^{-i pi j^2/n}.
+template <int FMT>
+__global__ void bluestein_pre_kernel(const void *in, float2 *a, const float2 *__restrict__ chirp,
+                                     long long batches, int n, int m) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= batches * m) return;
+    const long long b = gid / m;
+    const int j = (int)(gid % m);
+    float2 v = make_float2(0.0f, 0.0f);
+    if (j < n) v = cmul(load_elem<FMT>(in, b * n + j), __ldg(chirp + j));
+    a[gid] = v;
+}
+__global__ void bluestein_mul_kernel(float2 *a, const float2 *__restrict__ bfft, long long batches, int m) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= batches * m) return;
+    const int j = (int)(gid % m);
+    // conj() here and in the post stage turn the second forward FFT into an inverse one
+    const float2 p = cmul(a[gid], __ldg(bfft + j));
+    a[gid] = make_float2(p.x, -p.y);
+}
+__global__ void bluestein_post_kernel(const float2 *a, float2 *out, const float2 *__restrict__ chirp,
+                                      long long batches, int n, int m, unsigned flags, float norm) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int out_len = (flags & SDR_FFT_RFFT) ? n - n / 2 : n;
+    if (gid >= batches * out_len) return;
+    const long long b = gid / out_len;
+    const int j = (int)(gid % out_len);
+    int k = j;
+    if (!(flags & SDR_FFT_RFFT) && (flags & SDR_FFT_SHIFT)) {
+        k = j - n / 2;
+        if (k < 0) k += n;
+    }
+    const float2 y = a[b * m + k];
+    const float inv_m = 1.0f / (float)m;
+    float2 v = cmul(make_float2(y.x * inv_m, -y.y * inv_m), __ldg(chirp + k));
+    if (flags & SDR_FFT_NORM) { v.x *= norm; v.y *= norm; }
+    out[gid] = v;
+}
+
+int bluestein_pre_launch(const void *in, float2 *a, const float2 *chirp, long long batches, int n, int m, int fmt,
+                         cudaStream_t st) {
+    const long long total = batches * m;
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (fmt == SDR_FMT_U8IQ) bluestein_pre_kernel<SDR_FMT_U8IQ><<<grid, 256, 0, st>>>(in, a, chirp, batches, n, m);
+    else if (fmt == SDR_FMT_C64) bluestein_pre_kernel<SDR_FMT_C64><<<grid, 256, 0, st>>>(in, a, chirp, batches, n, m);
+    else bluestein_pre_kernel<SDR_FMT_F32><<<grid, 256, 0, st>>>(in, a, chirp, batches, n, m);
+    count_launch();
+    return launch_status();
+}
+int bluestein_mul_launch(float2 *a, const float2 *bfft, long long batches, int m, cudaStream_t st) {
+    const long long total = batches * m;
+    bluestein_mul_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, bfft, batches, m);
+    count_launch();
+    return launch_status();
+}
+int bluestein_post_launch(const float2 *a, float2 *out, const float2 *chirp, long long batches, int n, int m,
+                          unsigned flags, float norm, cudaStream_t st) {
+    const int out_len = (flags & SDR_FFT_RFFT) ? n - n / 2 : n;
+    const long long total = batches * out_len;
+    bluestein_post_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, out, chirp, batches, n, m, flags, norm);
+    count_launch();
+    return launch_status();
+}
+
+}  // namespace sdr

@@ -1,0 +1,94 @@
+// kernels.h -- internal launch interface between the C-ABI layer (api.cu) and the kernel files.
+#pragma once
+#include "common.cuh"
+
+namespace sdr {
+
+// ---------------------------------------------------------------------------------------
+// FIR (fir.cu)
+// ---------------------------------------------------------------------------------------
+struct FirArgs {
+    const void *in;    // n_ch rows of n_in elements (raw input format)
+    const void *hist;  // n_ch rows of HL elements, raw input format; hist[HL-1] is the newest
+    void *out;         // n_ch rows of n_out elements (c64 or f32)
+    const float *taps; // device; Kp entries (real) or Kp (re,im) pairs, zero padded beyond K
+    long long n_in, in_stride, out_stride, hist_stride, n_out;
+    long long first;   // index (in new-input coordinates) of the first kept output
+    int K, Kp, HL, D, n_ch;
+};
+// fmt: sdr_format_t.  Picks the register-blocked kernel when D == 1 and alignment allows,
+// the generic one otherwise.  *path: 1 = direct (FMA), 2 = strict order.
+int fir_launch(const FirArgs &a, int fmt, bool taps_complex, bool strict, cudaStream_t st, int *path);
+// hist_new = last HL elements of concat(hist_old, in[0..n_in))
+int fir_hist_update(const void *in, const void *hist_old, void *hist_new, int fmt, int HL, long long n_in,
+                    long long in_stride, long long hist_stride, int n_ch, cudaStream_t st);
+int fir_fill_hist(void *hist, int fmt, long long n_elems, cudaStream_t st);  // "zero" samples (128 for u8)
+
+int unpack_launch(const uint8_t *iq, size_t n, float *out, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// FFT (fft.cu)
+// ---------------------------------------------------------------------------------------
+struct FftArgs {
+    const void *in;
+    float2 *out;
+    const float2 *tw;   // W_n^k, k in [0, n)  (device)
+    long long batches;
+    int log_n;          // n = 1 << log_n, 4 <= log_n <= 16
+    int fmt;            // sdr_format_t
+    unsigned flags;     // SDR_FFT_*
+    float norm;         // 1.0f / sqrtf((float)n)
+};
+int fft_pow2_launch(const FftArgs &a, cudaStream_t st);
+// direct O(n^2) DFT for tiny / odd sizes handled without Bluestein (n <= 64)
+int fft_naive_launch(const void *in, float2 *out, const float2 *tw, long long batches, int n, int fmt,
+                     unsigned flags, float norm, cudaStream_t st);
+// Bluestein helpers: a[j] = x[j] * chirp[j] (zero padded to m), and the final pointwise stage
+int bluestein_pre_launch(const void *in, float2 *a, const float2 *chirp, long long batches, int n, int m,
+                         int fmt, cudaStream_t st);
+int bluestein_mul_launch(float2 *a, const float2 *bfft, long long batches, int m, cudaStream_t st);
+int bluestein_post_launch(const float2 *a, float2 *out, const float2 *chirp, long long batches, int n, int m,
+                          unsigned flags, float norm, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// PLL (pll.cu)
+// ---------------------------------------------------------------------------------------
+struct PllParams {      // per stream, device resident
+    float reference;    // already divided by rate (pll.rs:51)
+    float gain, rate;
+    float lc[5], oc[5], kc[5];  // loop / output / lock biquad coefficients b0,b1,b2,na1,na2
+    int lk, ok, kk;             // 0 = Identity
+};
+struct PllState {       // per stream, device resident
+    float nphase, vre, vim;
+    float lx1r, lx1i, lx2r, lx2i, ly1r, ly1i, ly2r, ly2i;  // loop filter (complex)
+    float ox1, ox2, oy1, oy2;                              // output filter
+    float kx1, kx2, ky1, ky2;                              // lock filter
+};
+int pll_launch(const float2 *in, long long n, long long in_stride, float *out, uint8_t *locked,
+               long long out_stride, const PllParams *params, int params_shared, PllState *state,
+               int n_streams, bool fast_math, cudaStream_t st);
+
+// ---------------------------------------------------------------------------------------
+// resampler (resample.cu)
+// ---------------------------------------------------------------------------------------
+struct SrcLaunch {
+    const float *v;     // device: carried frames followed by this call's input frames (interleaved)
+    long long have;     // frames in v
+    long long origin;   // frame index f (in the position's coordinate system) lives at v[f + origin]
+    float *out;
+    long long n_out;    // frames to produce
+    int channels, type;
+    double pos, step;   // output m sits at pos + m*step
+    // sinc only
+    const float *table; // device half table (half_len + 2 entries)
+    long long half_len;
+    double rq, rho;
+    long long wc;
+};
+int src_launch(const SrcLaunch &s, cudaStream_t st);
+// the windowed-sinc half table of converter `type` (0..2), computed once on the host in f64
+size_t src_sinc_table_host(int type, const float **table, int *increment);
+double src_sinc_wing(int type, double ratio, double *rq, double *rho, long long *wc);
+
+}  // namespace sdr
