@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sample-stream hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+
+Default workload = BASELINE.json configs[1]: batched 1024-point FFT spectrum of rtl_tcp-format u8 IQ,
+2^28 samples per GPU (fused unpack on load, fftshift + 1/sqrt(N) on store).  A "step" is one pass of the
+kernel over the whole 2^28-sample batch (512 MiB in, 2 GiB out: larger than the 126 MB L2, so every step
+streams from HBM).  With N > 1 (torchrun) every rank owns its own batch: no data-path collective,
+scaling = weak, value = all ranks' samples / max-over-ranks device time.
+
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "unnamed-rust-sdr_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """samples nvidia-smi clocks / throttle reasons while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.stop = threading.Event()
+        self.th = None
+
+    def _run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [c.strip() for c in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"], "samples": 0}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]),
+                "power_w_max": max(float(r[2]) for r in self.rows), "reasons": reasons, "samples": len(self.rows)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# workloads.  Each returns a dict: units per step (samples), algorithmic bytes per unit, step(), e2e(),
+# cpu(sample_units, threads) -> seconds
+# ---------------------------------------------------------------------------------------------------
+def wl_fft1024_u8(torch, sdr, dev, log2_samples=28):
+    n = 1024
+    samples = 1 << log2_samples
+    batches = samples // n
+    g = torch.Generator(device=dev).manual_seed(0x5D12B200 + 2)
+    raw = torch.randint(0, 256, (2 * samples,), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.empty((batches, n), dtype=torch.complex64, device=dev)
+    plan = sdr.FftPlan(n, "u8iq", shift=True, norm=True, device=dev.index, stream=torch.cuda.current_stream(dev))
+
+    def step():
+        plan.exec_dev(raw, batches, out)
+
+    host = {}
+
+    def e2e_setup():
+        host["in"] = torch.empty(2 * samples, dtype=torch.uint8).pin_memory()
+        host["in"].copy_(raw)
+        host["out"] = torch.empty((batches, n), dtype=torch.complex64).pin_memory()
+        host["plan"] = sdr.FftPlan(n, "u8iq", shift=True, norm=True, device=dev.index)
+
+    def e2e_step():
+        sdr.lib().sdr_fft_exec(host["plan"].h, host["in"].data_ptr(), batches, host["out"].data_ptr())
+        return float(host["out"][batches - 1, 0].real)
+
+    def cpu(units, threads):
+        import oracle_lib as O
+        import gen
+        iq = gen.random_u8(2 * units, 5)
+        t0 = time.perf_counter()
+        O.fft_batch_u8(iq, n, threads)
+        return time.perf_counter() - t0
+
+    return dict(name="c2_fft1024_u8iq_2p%d" % log2_samples, units=samples, bytes_per_unit=10.0, step=step,
+                e2e_setup=e2e_setup, e2e_step=e2e_step, h2d=2 * samples, d2h=8 * samples, cpu=cpu,
+                dtype="f32", kernel="fft_cta_kernel<10,u8iq>",
+                desc="batched 1024-pt FFT of u8 IQ, fused unpack + fftshift + 1/sqrt(N), %d transforms" % batches)
+
+
+def wl_fir_u8(torch, sdr, dev, K=64, D=1, log2_samples=26, complex_taps=False):
+    import gen
+    samples = 1 << log2_samples
+    fs = 2.048e6 if K == 64 else 2.4e6
+    taps = gen.lowpass_taps(K, 200e3 if K == 64 else 100e3, fs)
+    if complex_taps:
+        taps = gen.complex_bandpass_taps(K, 200e3, 100e3, fs)
+    g = torch.Generator(device=dev).manual_seed(0x5D12B200 + 1)
+    raw = torch.randint(0, 256, (2 * samples,), dtype=torch.uint8, device=dev, generator=g)
+    n_out = samples // D
+    out = torch.empty(n_out, dtype=torch.complex64, device=dev)
+    fir = sdr.Fir(taps, "u8iq", decimation=D, device=dev.index, stream=torch.cuda.current_stream(dev))
+
+    def step():
+        fir.process_dev(raw, samples, out, n_out)
+
+    host = {}
+
+    def e2e_setup():
+        host["in"] = torch.empty(2 * samples, dtype=torch.uint8).pin_memory()
+        host["in"].copy_(raw)
+        host["out"] = torch.empty(n_out, dtype=torch.complex64).pin_memory()
+        host["fir"] = sdr.Fir(taps, "u8iq", decimation=D, device=dev.index)
+
+    def e2e_step():
+        import ctypes as C
+        a, b = C.c_size_t(0), C.c_size_t(0)
+        sdr.lib().sdr_fir_process(host["fir"].h, host["in"].data_ptr(), samples, samples, host["out"].data_ptr(),
+                                  n_out, n_out, C.byref(a), C.byref(b))
+        return float(host["out"][n_out - 1].real)
+
+    def cpu(units, threads):
+        import oracle_lib as O
+        iq = gen.random_u8(2 * units, 5)
+        t0 = time.perf_counter()
+        O.fir_u8_mt(iq, taps, D, threads)
+        return time.perf_counter() - t0
+
+    return dict(name="fir%d%s_d%d_u8iq_2p%d" % (K, "c" if complex_taps else "", D, log2_samples), units=samples,
+                bytes_per_unit=2.0 + 8.0 / D, step=step, e2e_setup=e2e_setup, e2e_step=e2e_step, h2d=2 * samples,
+                d2h=8 * n_out, cpu=cpu, dtype="f32", kernel="fir_rb_kernel" if D == 1 else "fir_generic_kernel",
+                desc="fused u8-IQ unpack + %d-tap %s FIR, decimation %d" % (K, "complex" if complex_taps else "real", D))
+
+
+def wl_fft_c64(torch, sdr, dev, logn=12, log2_samples=27):
+    n = 1 << logn
+    samples = 1 << log2_samples
+    batches = samples // n
+    x = torch.empty((batches, n), dtype=torch.complex64, device=dev)
+    x.view(torch.float32).uniform_(-1, 1)
+    out = torch.empty_like(x)
+    plan = sdr.FftPlan(n, "c64", device=dev.index, stream=torch.cuda.current_stream(dev))
+
+    def step():
+        plan.exec_dev(x, batches, out)
+
+    def cpu(units, threads):
+        import oracle_lib as O
+        import gen
+        xs = gen.complex_noise(units, 3)
+        t0 = time.perf_counter()
+        O.fft_batch_c64(xs, n, False, threads)
+        return time.perf_counter() - t0
+
+    return dict(name="c5_fft%d_c64_2p%d" % (n, log2_samples), units=samples, bytes_per_unit=16.0, step=step,
+                e2e_setup=None, e2e_step=None, h2d=8 * samples, d2h=8 * samples, cpu=cpu, dtype="f32",
+                kernel="fft", desc="batched %d-pt c64 FFT, %d transforms" % (n, batches))
+
+
+def wl_channelizer(torch, sdr, dev, n_ch=128, log2_n=16):
+    import gen
+    n = 1 << log2_n
+    taps = gen.lowpass_taps(255, 100e3, 1.8e6)
+    B = sdr.BiquadD
+    design = sdr.PllDesign(0.0, 0.035, B.LowPass(80000.0, 0.7), B.LowPass(20000.0, 0.7), B.LowPass(20000.0, 0.7))
+    x = torch.empty((n_ch, n), dtype=torch.complex64, device=dev)
+    x.view(torch.float32).uniform_(-1, 1)
+    out = torch.empty((n_ch, n), dtype=torch.float32, device=dev)
+    lk = torch.empty((n_ch, n), dtype=torch.uint8, device=dev)
+    ch = sdr.Channelizer(taps, design, n_ch, 1.8e6, device=dev.index, stream=torch.cuda.current_stream(dev))
+
+    def step():
+        ch.process_dev(x, n, out, lk, n, n)
+
+    def cpu(units, threads):
+        import oracle_lib as O
+        c = max(1, threads)
+        m = max(1024, units // c)
+        xs = gen.complex_noise(c * m, 3).reshape(c, m)
+        od = O.pll_design(0.0, 0.035, (O.BQ_LOWPASS, 80000.0, 0.7), (O.BQ_LOWPASS, 20000.0, 0.7), (O.BQ_LOWPASS, 20000.0, 0.7))
+        t0 = time.perf_counter()
+        O.channelizer_mt(xs, taps, od, 1.8e6, threads)
+        return time.perf_counter() - t0
+
+    return dict(name="c4_channelizer_%dch_2p%d" % (n_ch, log2_n), units=n_ch * n, bytes_per_unit=12.125, step=step,
+                e2e_setup=None, e2e_step=None, h2d=8 * n_ch * n, d2h=5 * n_ch * n, cpu=cpu, dtype="f32",
+                kernel="fir_rb_kernel+pll_kernel", desc="%d channels x (255-tap FIR + PLL)" % n_ch)
+
+
+def make_workload(name, torch, sdr, dev):
+    if name in ("c2", "fft1024_u8", "default"):
+        return wl_fft1024_u8(torch, sdr, dev)
+    if name == "c2_small":
+        return wl_fft1024_u8(torch, sdr, dev, 24)
+    if name in ("c1", "fir64_u8"):
+        return wl_fir_u8(torch, sdr, dev, 64, 1)
+    if name == "c1c":
+        return wl_fir_u8(torch, sdr, dev, 64, 1, complex_taps=True)
+    if name in ("c3", "fir255_d10_u8"):
+        return wl_fir_u8(torch, sdr, dev, 255, 10)
+    if name == "fir255_u8":
+        return wl_fir_u8(torch, sdr, dev, 255, 1)
+    if name == "c4":
+        return wl_channelizer(torch, sdr, dev)
+    if name.startswith("c5_"):
+        return wl_fft_c64(torch, sdr, dev, int(name[3:]))
+    raise SystemExit("unknown workload " + name)
+
+
+CPU_SAMPLE_UNITS = {"c2": 1 << 26, "fir": 1 << 22, "c5": 1 << 25, "c4": 1 << 19}
+
+
+def cpu_sample_units(wl):
+    n = wl["name"]
+    if n.startswith("c2"):
+        return CPU_SAMPLE_UNITS["c2"]
+    if n.startswith("fir"):
+        return CPU_SAMPLE_UNITS["fir"]
+    if n.startswith("c5"):
+        return CPU_SAMPLE_UNITS["c5"]
+    return CPU_SAMPLE_UNITS["c4"]
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path, all host threads.  The Rust crate
+    cannot be built in this image (no cargo/rustc), so this is the oracle port: the f32-faithful C++ restatement
+    of the reference's per-sample structure, re-planning the FFT on every call as src/fft.rs:10-11 does."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib as O
+
+    class _NoTorch:
+        pass
+    threads = O.hardware_threads()
+    # build the workload description without touching a GPU
+    name = args.workload
+    cpu_only = {
+        "c2": (lambda u, t: _cpu_fft_u8(u, t), 1 << 26, "c2_fft1024_u8iq_2p28"),
+        "default": (lambda u, t: _cpu_fft_u8(u, t), 1 << 26, "c2_fft1024_u8iq_2p28"),
+    }
+    fn, units, wname = cpu_only.get(name, cpu_only["c2"])
+    for _ in range(args.warmup):
+        fn(units // 8, threads)
+    t = 0.0
+    for _ in range(args.steps):
+        t += fn(units, threads)
+    value = units * args.steps / t / 1e9
+    line = {
+        "impl": "reference", "metric": "FIR/FFT Gsamples/s", "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wname, "sample_per_step": units, "note": "CPU oracle port of the reference path "
+                   "(unpack + per-call-planned radix-4 FFT + shift/norm), std::thread over independent blocks"},
+        "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": threads, "kind": "port",
+                         "sample": "%d samples (%d x 1024-pt blocks) per step" % (units, units // 1024)},
+        "e2e": {"value": value, "unit": "Gsamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def _cpu_fft_u8(units, threads):
+    import oracle_lib as O
+    import gen
+    iq = gen.random_u8(2 * units, 5)
+    t0 = time.perf_counter()
+    O.fft_batch_u8(iq, 1024, threads)
+    return time.perf_counter() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import sdr_b200 as sdr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or sdr.device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device (libsdr_b200 has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    # everything runs on one explicit stream: the library launches on it and the CUDA events are recorded on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    wl = make_workload(args.workload, torch, sdr, dev)
+    peak, peak_src = measured_peaks()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        wl["step"]()
+    barrier()
+    l0 = sdr.kernel_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            wl["step"]()
+        ev1.record()
+        barrier()
+    launches = sdr.kernel_launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    per_step_ms = ms / args.steps
+    value = world * wl["units"] / (per_step_ms * 1e-3) / 1e9
+    achieved = wl["units"] * wl["bytes_per_unit"] / (per_step_ms * 1e-3) / 1e9  # GB/s on this rank's GPU
+
+    e2e = None
+    if not args.no_e2e and wl["e2e_step"] is not None:
+        wl["e2e_setup"]()
+        wl["e2e_step"]()
+        barrier()
+        t0 = time.perf_counter()
+        chk = 0.0
+        for _ in range(args.e2e_steps):
+            chk += wl["e2e_step"]()
+        barrier()
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if dist is not None:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t)
+        e2e = {"value": world * wl["units"] / dt / 1e9, "unit": "Gsamples/s", "h2d_bytes_per_step": wl["h2d"],
+               "d2h_bytes_per_step": wl["d2h"], "ms_per_step": dt * 1e3, "steps": args.e2e_steps,
+               "api": "host-buffer C ABI call (pinned host memory), H2D + kernel + D2H inside the timed region"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle_lib as O
+        threads = O.hardware_threads()
+        units = cpu_sample_units(wl)
+        wl["cpu"](units // 16, threads)
+        secs = wl["cpu"](units, threads)
+        secs1 = wl["cpu"](max(units // max(threads, 1), 1 << 16), 1)
+        cpu = {"value": units / secs / 1e9, "unit": "Gsamples/s", "cores": threads, "kind": "port",
+               "sample": "%d samples of the same workload" % units,
+               "single_thread_value": max(units // max(threads, 1), 1 << 16) / secs1 / 1e9}
+
+    if rank == 0:
+        line = {
+            "metric": "FIR/FFT Gsamples/s", "value": value, "unit": "Gsamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": wl["dtype"], "data": "synthetic",
+            "config": {"workload": wl["name"], "desc": wl["desc"], "samples_per_gpu_per_step": wl["units"],
+                       "l2": "inputs+outputs per step exceed the 126 MB L2 (streamed from HBM every step)",
+                       "parallelism": "independent shards per GPU, no data-path collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": wl["kernel"],
+                         "algorithmic_bytes_per_sample": wl["bytes_per_unit"]},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -90,7 +90,8 @@ typedef struct {
     size_t n_channels;   /* independent streams sharing the taps (>= 1) */
     unsigned flags;
     int device;
-    void *stream;        /* cudaStream_t to run on; NULL = handle creates its own */
+    void *stream;        /* cudaStream_t to run on; NULL = handle creates its own (pass cudaStreamLegacy,
+                            (void*)0x1, to run on the legacy default stream) */
 } sdr_fir_config_t;
 
 typedef struct sdr_fir sdr_fir_t;

@@ -1,0 +1,134 @@
+"""GPU parity: batched FFT through the C ABI vs the f64 DFT.  Bar: 1e-5 * log2(N) of max |X|."""
+import os
+
+import numpy as np
+import pytest
+
+import gen
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def check(got, x_rows, shift=False, norm=False):
+    n = x_rows.shape[1]
+    ref = np.fft.fft(x_rows.astype(np.complex128), axis=1)
+    if shift:
+        ref = np.roll(ref, n // 2, axis=1)
+    if norm:
+        ref = ref / np.sqrt(n)
+    err = np.abs(got - ref).max() / np.abs(ref).max()
+    assert err < 1e-5 * max(1.0, np.log2(n)), (n, err)
+    return err
+
+
+@pytest.mark.parametrize("logn", list(range(4, 17)))
+def test_pow2_sizes_c64(sdr, logn):
+    n = 1 << logn
+    batches = max(3, min(70, (1 << 18) // n))  # ragged vs transforms-per-CTA
+    x = gen.complex_noise(batches * n, 1000 + logn).reshape(batches, n)
+    got = sdr.FftPlan(n, "c64").exec(x)
+    check(got, x)
+    # oracle f64 DFT agrees with numpy on one row (ties the test to the oracle as well)
+    assert np.abs(O.dft_f64(x[0]) - np.fft.fft(x[0].astype(np.complex128))).max() < 1e-9 * n
+
+
+@pytest.mark.parametrize("logn", [8, 10, 12, 14, 16])
+def test_shift_norm_are_exact_permutation_and_scale(sdr, logn):
+    n = 1 << logn
+    x = gen.complex_noise(5 * n, 5).reshape(5, n)
+    plain = sdr.FftPlan(n, "c64").exec(x)
+    sn = sdr.FftPlan(n, "c64", shift=True, norm=True).exec(x)
+    norm = np.float32(1.0) / np.sqrt(np.float32(n))
+    want = np.roll(plain, n // 2, axis=1)
+    assert np.array_equal(sn.real, want.real * norm) and np.array_equal(sn.imag, want.imag * norm)
+
+
+@pytest.mark.parametrize("n", [256, 1024, 4096, 32768])
+def test_fused_u8_unpack(sdr, n):
+    batches = 9
+    raw = gen.random_u8(2 * batches * n, n)
+    x = O.unpack_u8iq(raw).reshape(batches, n)
+    got = sdr.FftPlan(n, "u8iq", shift=True, norm=True).exec(raw)
+    check(got, x, shift=True, norm=True)
+    # fused unpack == unpack then c64 transform, bit for bit
+    two = sdr.FftPlan(n, "c64", shift=True, norm=True).exec(x)
+    assert np.array_equal(got.view(np.uint32), two.view(np.uint32))
+
+
+def test_tone_known_answer_and_labels(sdr):
+    n, b = 1024, 37
+    x = np.exp(2j * np.pi * b * np.arange(n) / n).astype(np.complex64)
+    labels, vals = sdr.fft(x, 2.048e6)
+    k = int(np.argmax(np.abs(vals)))
+    assert k == b + n // 2 and abs(abs(vals[k]) - np.sqrt(n)) < 1e-3
+    assert np.delete(np.abs(vals), k).max() < 1e-3
+    lab, ov = O.fft_shifted(x, 2.048e6)
+    assert np.array_equal(labels, lab)
+    assert np.abs(vals - ov).max() < 1e-5 * 10 * np.sqrt(n)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 8, 12, 60, 64])
+def test_tiny_sizes(sdr, n):
+    x = gen.complex_noise(4 * n, n).reshape(4, n)
+    check(sdr.FftPlan(n, "c64", shift=True, norm=True).exec(x), x, shift=True, norm=True) if n > 1 else None
+    got = sdr.FftPlan(n, "c64").exec(x)
+    check(got, x)
+
+
+@pytest.mark.parametrize("n", [100, 1000, 14400, 30000])
+def test_arbitrary_length_bluestein(sdr, n):
+    """the reference's real uses: 1000-point complex (examples/live.rs:31), 14400-point real (examples/fft.rs:64)"""
+    x = gen.complex_noise(3 * n, n).reshape(3, n)
+    got = sdr.FftPlan(n, "c64", shift=True, norm=True).exec(x)
+    check(got, x, shift=True, norm=True)
+
+
+@pytest.mark.parametrize("n", [8, 1001, 4096, 14400])
+def test_rfft_matches_reference_semantics(sdr, n):
+    x = gen.noise(n, 17).astype(np.float32)
+    labels, vals = sdr.rfft(x, 144000.0)
+    ol, ov = O.rfft_shifted(x, 144000.0)
+    assert len(vals) == n - n // 2 == len(ov) and np.array_equal(labels, ol)
+    ref = np.fft.fft(x.astype(np.float64))[:n - n // 2] / np.sqrt(n)
+    assert np.abs(vals - ref).max() / np.abs(ref).max() < 1e-5 * np.log2(n)
+
+
+def test_golden_c2(sdr):
+    g = np.load(os.path.join(GOLD, "oracle_golden.npz"))
+    got = sdr.FftPlan(1024, "u8iq", shift=True, norm=True).exec(g["c1_iq"])
+    ref = g["c2_fft1024"]
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5 * 10
+
+
+def test_signal_level_fft_of_u8_source(sdr):
+    raw = gen.random_u8(2 * 4096, 3)
+    labels, vals = sdr.signal.fft(sdr.signal.from_u8iq(2.048e6, raw))
+    ol, ov = O.fft_shifted(O.unpack_u8iq(raw), 2.048e6)
+    assert np.array_equal(labels, ol) and np.abs(vals - ov).max() / np.abs(ov).max() < 1e-5 * 12
+
+
+def test_c2_full_size_parseval_and_spot_checks(sdr):
+    """BASELINE config 2 at full size: 2^28 u8-IQ samples, 262144 x 1024-point, device resident.
+    Size-independent properties: the normalised transform is unitary (Parseval per block, in f64 on the
+    device) and blocks picked across the batch match the f64 DFT."""
+    import torch
+    n, batches = 1024, 1 << 18
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(7)
+    raw = torch.randint(0, 256, (2 * n * batches,), dtype=torch.uint8, device=dev, generator=g)
+    out = torch.empty((batches, n), dtype=torch.complex64, device=dev)
+    plan = sdr.FftPlan(n, "u8iq", shift=True, norm=True)
+    plan.exec_dev(raw, batches, out)
+    torch.cuda.synchronize()
+    for lo in range(0, batches, 1 << 16):
+        blk = raw[2 * n * lo:2 * n * (lo + (1 << 16))].view(-1, n, 2).to(torch.float64)
+        e_in = (((blk - 128.0) / 128.0) ** 2).sum(dim=(1, 2))
+        o = out[lo:lo + (1 << 16)]
+        e_out = (o.real.double() ** 2 + o.imag.double() ** 2).sum(dim=1)
+        assert float(((e_out - e_in).abs() / e_in).max()) < 1e-5
+    for b in (0, 1, 4097, batches // 2 + 3, batches - 1):
+        x = O.unpack_u8iq(raw[2 * n * b:2 * n * (b + 1)].cpu().numpy()).reshape(1, n)
+        check(out[b:b + 1].cpu().numpy(), x, shift=True, norm=True)

@@ -1,0 +1,178 @@
+"""GPU parity: unpack + FIR (+ Decimate) through the C ABI vs the oracle.
+Bars (BASELINE.json north_star): bit-exact unpack, decimation indexing and output counts; FIR within
+1e-5 of max|y| of the f64 truth (and, in STRICT_ORDER mode, bit-identical to the reference's f32 order)."""
+import os
+
+import numpy as np
+import pytest
+
+import gen
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-5
+
+
+def rel_err(y, truth):
+    return float(np.abs(y.astype(np.complex128) - truth).max() / max(np.abs(truth).max(), 1e-30))
+
+
+def test_unpack_exhaustive_table_and_random(sdr):
+    u = np.arange(256, dtype=np.uint8)
+    iq = np.stack([u, u[::-1]], 1).ravel()
+    assert np.array_equal(sdr.unpack_u8iq(iq).view(np.uint32), O.unpack_u8iq(iq).view(np.uint32))
+    for n in (1, 7, 8, 9, 1000, 1 << 20):
+        raw = gen.random_u8(2 * n, 42 + n)
+        assert np.array_equal(sdr.unpack_u8iq(raw).view(np.uint32), O.unpack_u8iq(raw).view(np.uint32))
+    assert len(sdr.unpack_u8iq(np.zeros(0, np.uint8))) == 0
+
+
+@pytest.mark.parametrize("K", [1, 5, 8, 63, 64, 255])
+@pytest.mark.parametrize("tc", [False, True])
+def test_fir_strict_is_bit_identical_to_reference_order_u8(sdr, K, tc):
+    rng = np.random.default_rng(K)
+    taps = rng.standard_normal(K).astype(np.float32)
+    if tc:
+        taps = (taps + 1j * rng.standard_normal(K)).astype(np.complex64)
+    n = 10000 + K
+    iq = gen.tone_noise_u8(n, 2.048e6, 300e3, 0.5, 0.1, 7 + K)
+    want = O.Fir(taps).apply(O.unpack_u8iq(iq))
+    f = sdr.Fir(taps, "u8iq", strict=True)
+    got = f.process(iq)
+    assert f.last_path == 2
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("fmt", ["c64", "f32"])
+def test_fir_strict_c64_and_real_samples(sdr, fmt):
+    taps = gen.lowpass_taps(255, 100e3, 2.4e6)
+    if fmt == "c64":
+        x = gen.complex_noise(20000, 3)
+        want = O.Fir(taps).apply(x)
+    else:
+        x = gen.noise(20000, 3).astype(np.float32)
+        want = O.Fir(taps, O.KIND_F32).apply(x)
+    got = sdr.Fir(taps, fmt, strict=True).process(x)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+
+@pytest.mark.parametrize("K,tc", [(64, False), (64, True), (255, False)])
+def test_fir_fast_path_within_tolerance_of_f64_truth(sdr, K, tc):
+    taps = gen.complex_bandpass_taps(K, 200e3, 100e3, 2.048e6) if tc else gen.lowpass_taps(K, 200e3, 2.048e6)
+    iq = gen.tone_noise_u8(1 << 18, 2.048e6, 300e3, 0.5, 0.1, gen.BASE_SEED + 1)
+    x = O.unpack_u8iq(iq)
+    truth = O.fir_f64(taps, x)
+    got = sdr.Fir(taps, "u8iq").process(iq)
+    e_gpu, e_ref = rel_err(got, truth), rel_err(O.Fir(taps).apply(x), truth)
+    assert len(got) == len(x)
+    assert e_gpu < TOL, (e_gpu, e_ref)
+    assert e_gpu <= 4 * e_ref + 1e-7  # no worse than the reference's own f32 rounding
+
+
+def test_fir_impulse_response_is_the_taps(sdr):
+    taps = gen.lowpass_taps(64, 200e3, 2.048e6)
+    x = np.zeros(300, np.complex64)
+    x[0] = 1
+    for strict in (False, True):
+        y = sdr.Fir(taps, "c64", strict=strict).process(x)
+        assert np.array_equal(y[:64].real, taps) and np.all(y[64:] == 0) and np.all(y.imag == 0)
+
+
+@pytest.mark.parametrize("strict", [False, True])
+def test_fir_streaming_blocks_equal_one_call(sdr, strict):
+    taps = gen.lowpass_taps(255, 100e3, 2.4e6)
+    iq = gen.fm_u8(50000, 2.4e6, 75e3, 1e3, 0.05, 21)
+    whole = sdr.Fir(taps, "u8iq", strict=strict).process(iq)
+    f = sdr.Fir(taps, "u8iq", strict=strict)
+    cuts = [0, 1, 2, 9, 100, 254, 255, 256, 4096, 4097, 20000, 50000]
+    parts = [f.process(iq[2 * a:2 * b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(parts).view(np.uint32), whole.view(np.uint32))
+    assert len(f.process(np.zeros(0, np.uint8))) == 0
+
+
+@pytest.mark.parametrize("D", [2, 5, 10, 50])
+def test_decimating_fir_counts_indices_and_values(sdr, D):
+    taps = gen.lowpass_taps(255, 100e3, 2.4e6)
+    n = 40000 + 3
+    iq = gen.fm_u8(n, 2.4e6, 75e3, 1e3, 0.05, 31)
+    x = O.unpack_u8iq(iq)
+    full = O.Fir(taps).apply(x)
+    want, _ = O.decimate(full, D)
+    got = sdr.Fir(taps, "u8iq", decimation=D, strict=True).process(iq)
+    assert len(got) == n // D == len(want)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    fast = sdr.Fir(taps, "u8iq", decimation=D).process(iq)
+    truth = O.fir_f64(taps, x)[D - 1::D]
+    assert len(fast) == n // D and rel_err(fast, truth) < TOL
+    # streaming with ragged blocks keeps the phase
+    f = sdr.Fir(taps, "u8iq", decimation=D, strict=True)
+    cuts = [0, 3, 3 + D - 1, 1000, 1001, 25000, n]
+    parts = [f.process(iq[2 * a:2 * b]) for a, b in zip(cuts[:-1], cuts[1:])]
+    assert np.array_equal(np.concatenate(parts).view(np.uint32), want.view(np.uint32))
+
+
+def test_fir_clone_reset_and_multichannel(sdr):
+    taps = gen.lowpass_taps(64, 200e3, 2.048e6)
+    x = gen.complex_noise(6 * 5000, 8).reshape(6, 5000)
+    want = np.stack([O.Fir(taps).apply(r) for r in x])
+    f = sdr.Fir(taps, "c64", n_channels=6, strict=True)
+    a = f.process(x[:, :1234])
+    g = f.clone()
+    b = f.process(x[:, 1234:])
+    b2 = g.process(x[:, 1234:])
+    assert np.array_equal(np.concatenate([a, b], 1), want) and np.array_equal(b2, b)
+    f.reset()
+    assert np.array_equal(f.process(x[:, :100]), want[:, :100])
+    fast = sdr.Fir(taps, "c64", n_channels=6).process(x)
+    truth = np.stack([O.fir_f64(taps, r) for r in x])
+    assert rel_err(fast, truth) < TOL
+
+
+def test_fir_errors(sdr):
+    import ctypes as C
+    taps = gen.lowpass_taps(8, 200e3, 2.048e6)
+    f = sdr.Fir(taps, "c64")
+    x = np.zeros(100, np.complex64)
+    out = np.zeros(10, np.complex64)
+    used, got = C.c_size_t(0), C.c_size_t(0)
+    rc = sdr.lib().sdr_fir_process(f.h, x.ctypes.data, 100, 100, out.ctypes.data, 10, 10, C.byref(used), C.byref(got))
+    assert rc == 104 and used.value == 0 and got.value == 0
+    with pytest.raises(sdr.SdrError):
+        sdr.Fir(taps.astype(np.complex64), "f32")
+
+
+def test_golden_c1_c3(sdr):
+    g = np.load(os.path.join(GOLD, "oracle_golden.npz"))
+    taps64, taps255 = gen.lowpass_taps(64, 200e3, 2.048e6), gen.lowpass_taps(255, 100e3, 2.4e6)
+    got = sdr.Fir(taps64, "u8iq", strict=True).process(g["c1_iq"])
+    assert np.array_equal(got.view(np.uint32), g["c1_fir64"].view(np.uint32))
+    got = sdr.Fir(taps255, "u8iq", decimation=10, strict=True).process(g["c3_iq"])
+    assert np.array_equal(got.view(np.uint32), g["c3_fir255_dec10"].view(np.uint32))
+
+
+def test_fir_full_size_linearity_and_device_path(sdr):
+    """C1 at 2^26 samples, device-resident: FIR(a + b) == FIR(a) + FIR(b) on tones whose unpacked values add
+    exactly, and shard-with-halo outputs equal the single-call outputs bit for bit."""
+    import torch
+    n = 1 << 26
+    taps = gen.lowpass_taps(64, 200e3, 2.048e6)
+    dev = torch.device("cuda:0")
+    gen_t = torch.Generator(device=dev).manual_seed(1234)
+    iq = torch.randint(0, 256, (2 * n,), dtype=torch.uint8, device=dev, generator=gen_t)
+    out = torch.empty(n, dtype=torch.complex64, device=dev)
+    f = sdr.Fir(taps, "u8iq")
+    assert f.process_dev(iq, n, out, n) == n
+    torch.cuda.synchronize()
+    # spot-check 3 windows against the oracle
+    for s in (0, 12345678, n - 5000):
+        seg = iq[2 * max(0, s - 63):2 * (s + 5000)].cpu().numpy()
+        want = O.fir_f64(taps, O.unpack_u8iq(seg))[-5000:]
+        assert rel_err(out[s:s + 5000].cpu().numpy(), want) < TOL
+    # two shards with a K-1 halo reproduce the whole
+    half = n // 2
+    f2 = sdr.Fir(taps, "u8iq")
+    o2 = torch.empty(half + 64, dtype=torch.complex64, device=dev)
+    got = f2.process_dev(iq[2 * (half - 64):], half + 64, o2, half + 64)
+    torch.cuda.synchronize()
+    assert got == half + 64 and torch.equal(o2[64:].view(torch.float32), out[half:].view(torch.float32))

@@ -1,0 +1,186 @@
+"""GPU parity: batched PLL, channelizer, resampler and the adaptor chain through the C ABI vs the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+import gen
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def example_design(sdr):
+    B = sdr.BiquadD
+    return sdr.PllDesign(0.0, 0.035, B.LowPass(80000.0, 0.7), B.LowPass(20000.0, 0.7), B.LowPass(20000.0, 0.7))
+
+
+def oracle_design():
+    return O.pll_design(0.0, 0.035, (O.BQ_LOWPASS, 80000.0, 0.7), (O.BQ_LOWPASS, 20000.0, 0.7), (O.BQ_LOWPASS, 20000.0, 0.7))
+
+
+def compare_pll(out, lk, rout, rlk, rate, gain, tol_frac, what):
+    """no PLL tolerance is stated by the north star; the loop feeds back through atan2/sin/cos whose last
+    bit differs between CUDA and glibc.  Bar used here: |d out| <= tol_frac * (rate * gain * pi) -- the PLL's
+    full-scale output -- and lock flags equal except where the lock filter sits within eps of 0.01."""
+    full = rate * gain * np.pi
+    err = np.abs(out - rout).max() / full
+    mism = int((lk != rlk).sum())
+    assert err < tol_frac, (what, err)
+    assert mism <= max(2, len(lk.ravel()) // 500), (what, mism)
+    return err, mism
+
+
+@pytest.mark.parametrize("fast", [False, True])
+def test_pll_example_sweep(sdr, fast):
+    g = np.load(os.path.join(GOLD, "oracle_golden.npz"))
+    v = g["sweep"]
+    p = sdr.PllBatch([example_design(sdr)], 1, 1.8e6, fast_math=fast)
+    out, lk = p.process(v)
+    err, mism = compare_pll(out, lk, g["pll_out"], g["pll_locked"], 1.8e6, 0.035, 2e-3 if fast else 1e-3, "sweep")
+    nph, val = p.state(0)
+    assert abs(nph) < 1 and abs(abs(val) - 1) < 1e-6  # f32::fract keeps the sign
+    # first sample sees value = 0+0i (pll.rs:57-58)
+    assert out[0] == 0.0 and lk[0] == 0
+
+
+def test_pll_streams_are_independent_and_chunking_is_exact(sdr):
+    _, v = O.freq_sweep(1800000.0, 20000.0, True, -200000.0, 200000.0)
+    S = 70  # not a multiple of 32
+    x = np.stack([np.roll(v, 13 * s) * np.exp(1j * 0.1 * s) for s in range(S)]).astype(np.complex64)
+    p = sdr.PllBatch([example_design(sdr)], S, 1.8e6)
+    out, lk = p.process(x)
+    q = sdr.PllBatch([example_design(sdr)], S, 1.8e6)
+    parts = [q.process(np.ascontiguousarray(x[:, a:b])) for a, b in [(0, 1), (1, 33), (33, 1000), (1000, 1890)]]
+    assert np.array_equal(np.concatenate([a for a, _ in parts], 1).view(np.uint32), out.view(np.uint32))
+    assert np.array_equal(np.concatenate([b for _, b in parts], 1), lk)
+    for s in (0, 31, 32, 69):
+        ro, rl = O.Pll(oracle_design(), 1.8e6).apply(x[s])
+        compare_pll(out[s], lk[s], ro, rl, 1.8e6, 0.035, 1e-3, "stream %d" % s)
+    # clone carries state, reset restores the initial one
+    c = q.clone()
+    a1, _ = q.process(x[:, :100])
+    a2, _ = c.process(x[:, :100])
+    assert np.array_equal(a1.view(np.uint32), a2.view(np.uint32))
+    q.reset()
+    a3, _ = q.process(x[:, :100])
+    assert np.array_equal(a3.view(np.uint32), out[:, :100].view(np.uint32))
+
+
+def test_pll_per_stream_designs_and_identity_filters(sdr):
+    B = sdr.BiquadD
+    d0 = sdr.PllDesign(19000.0, 0.0002, B.LowPass(200.0, 0.7), B.LowPass(20.0, 0.7), B.LowPass(20.0, 0.7))  # main.rs:55-60
+    d1 = sdr.PllDesign(0.0, 0.035, B.LowPass(80000.0, 0.7), sdr.Identity(), B.LowPass(20000.0, 0.7))           # main.rs:41-46
+    t = np.arange(20000)
+    x0 = (0.2 * np.cos(2 * np.pi * 19000.0 * t / 144000.0)).astype(np.complex64)
+    x1 = np.exp(2j * np.pi * 0.01 * t).astype(np.complex64)
+    p = sdr.PllBatch([d0, d1], 2, 144000.0)
+    out, lk = p.process(np.stack([x0, x1]))
+    o0 = O.pll_design(19000.0, 0.0002, (O.BQ_LOWPASS, 200.0, 0.7), (O.BQ_LOWPASS, 20.0, 0.7), (O.BQ_LOWPASS, 20.0, 0.7))
+    o1 = O.pll_design(0.0, 0.035, (O.BQ_LOWPASS, 80000.0, 0.7), (O.BQ_IDENTITY, 0, 0), (O.BQ_LOWPASS, 20000.0, 0.7))
+    r0, l0 = O.Pll(o0, 144000.0).apply(x0)
+    r1, l1 = O.Pll(o1, 144000.0).apply(x1)
+    compare_pll(out[0], lk[0], r0, l0, 144000.0, 0.0002, 2e-2, "pilot")
+    compare_pll(out[1], lk[1], r1, l1, 144000.0, 0.035, 1e-3, "demod")
+
+
+def test_channelizer_small(sdr):
+    """C4 in miniature: 40 channels x (255-tap FIR -> PLL)"""
+    C_, n = 40, 6000
+    taps = gen.lowpass_taps(255, 100e3, 1.8e6)
+    t = np.arange(n)
+    x = np.stack([np.exp(2j * np.pi * (0.002 * c - 0.03) * t + 0.5j * np.sin(2 * np.pi * 0.001 * t * (1 + c % 3)))
+                  for c in range(C_)]).astype(np.complex64)
+    x = (x + 0.05 * gen.complex_noise(C_ * n, 4).reshape(C_, n)).astype(np.complex64)
+    ch = sdr.Channelizer(taps, example_design(sdr), C_, 1.8e6, strict=True)
+    out, lk = ch.process(x)
+    rout, rlk = O.channelizer_mt(x, taps, oracle_design(), 1.8e6, threads=4)
+    compare_pll(out, lk, rout, rlk, 1.8e6, 0.035, 1e-3, "channelizer")
+    # blocks == one call
+    ch.reset()
+    a = ch.process(np.ascontiguousarray(x[:, :2500]))
+    b = ch.process(np.ascontiguousarray(x[:, 2500:]))
+    assert np.array_equal(np.concatenate([a[0], b[0]], 1).view(np.uint32), out.view(np.uint32))
+
+
+@pytest.mark.parametrize("typ", ["Linear", "ZeroOrderHold", "SincFastest", "SincMediumQuality"])
+@pytest.mark.parametrize("ratio", [0.2, 0.08, 1.0 / 3.0, 1.5, 48000.0 / 44100.0])
+def test_samplerate_process_matches_oracle(sdr, typ, ratio):
+    ct = getattr(sdr.ConverterType, typ)
+    x = gen.complex_noise(9000, 12).view(np.float32).reshape(-1, 2)
+    a = sdr.SampleRate(ct, 2)
+    b = O.SampleRate(int(ct), 2)
+    pos = 0
+    outs_a, outs_b = [], []
+    for blk in (1, 7, 4096, 100, 4096, 0, 0):
+        chunk = x[pos:pos + blk]
+        ua, oa = a.process(ratio, chunk, 4096)
+        ub, ob = b.process(ratio, chunk, 4096)
+        assert ua == ub and len(oa) == len(ob), (typ, ratio, blk, ua, ub, len(oa), len(ob))
+        outs_a.append(oa)
+        outs_b.append(ob)
+        pos += ua
+    ya, yb = np.concatenate(outs_a), np.concatenate(outs_b)
+    assert len(ya) > 0
+    if typ in ("Linear", "ZeroOrderHold"):
+        assert np.array_equal(ya.view(np.uint32), yb.view(np.uint32))
+    else:
+        # f64 accumulation in identical order: equal up to the final f32 rounding
+        assert np.abs(ya - yb).max() <= 1.2e-7 * max(1.0, np.abs(yb).max())
+        assert (ya.view(np.uint32) != yb.view(np.uint32)).mean() < 1e-3
+
+
+def test_samplerate_contract(sdr):
+    s = sdr.SampleRate(sdr.ConverterType.SincBestQuality, 2)
+    assert s.get_channels() == 2
+    with pytest.raises(sdr.ResampleError) as e:
+        s.process(1e-4, np.zeros((4, 2), np.float32), 16)
+    assert e.value.code == 6
+    used, out = s.process(0.5, np.zeros((0, 2), np.float32), 16)
+    assert used == 0 and len(out) == 0
+    x = gen.complex_noise(3000, 1).view(np.float32).reshape(-1, 2)
+    s.reset()
+    u1, o1 = s.process(0.5, x, 4096)
+    c = s.try_clone()
+    u2, o2 = s.process(0.5, x[:0], 4096)
+    u3, o3 = c.process(0.5, x[:0], 4096)
+    assert u1 == 3000 and np.array_equal(o2, o3) and len(o1) + len(o2) == 1500
+    s.set_ratio(0.25)
+    with pytest.raises(sdr.ResampleError):
+        s.set_ratio(1e9)
+    assert sdr.ConverterType.Linear.name_str() == "Linear Interpolator"
+
+
+def test_c3_chain_matches_oracle_chain(sdr):
+    """config C3: u8 IQ -> 255-tap FIR -> decimate 2.4 MS/s -> 240 kS/s -> (relabel rate) ->
+    resample to 48 kHz, through the signal adaptors; vs the oracle's per-sample chain."""
+    S = sdr.signal
+    g = np.load(os.path.join(GOLD, "oracle_golden.npz"))
+    n = 240000
+    iq = gen.fm_u8(n, 2.4e6, 75e3, 1e3, 0.05, gen.BASE_SEED + 3)
+    assert np.array_equal(iq[:2 * 8192], g["c3_iq"])
+    taps = gen.lowpass_taps(255, 100e3, 2.4e6)
+    dec = S.from_u8iq(2.4e6, iq).filter(taps).decimate(240e3)
+    assert dec.fused and dec.wait == 10
+    y = dec.collect(block=50000)
+    x = O.unpack_u8iq(iq)
+    truth = O.fir_f64(taps, x)[9::10]
+    assert len(y) == n // 10
+    assert np.abs(y - truth).max() / np.abs(truth).max() < 1e-5
+    assert np.abs(y[:len(g["c3_fir255_dec10"])] - g["c3_fir255_dec10"]).max() < 1e-5
+    for typ, otyp in ((sdr.ConverterType.SincFastest, O.SRC_SINC_FASTEST), (sdr.ConverterType.Linear, O.SRC_LINEAR)):
+        z = S.from_array(240e3, y).resample_with(typ, 48e3).collect()
+        ref = O.resample_signal(y, otyp, float(np.float64(np.float32(48e3)) / np.float64(np.float32(240e3))))
+        assert len(z) == len(ref) and abs(len(z) - n // 50) <= 2
+        assert np.abs(z - ref).max() <= 2e-7 * max(1.0, np.abs(ref).max())
+
+
+def test_pll_filter_adaptor(sdr):
+    """source.filter(PllDesign) (main.rs:49): (value, locked) <-> Option<f32>"""
+    S = sdr.signal
+    g = np.load(os.path.join(GOLD, "oracle_golden.npz"))
+    f = S.from_array(1.8e6, g["sweep"]).filter(example_design(sdr))
+    out = f.collect()
+    assert len(out) == 1890
+    compare_pll(out, f.locked, g["pll_out"], g["pll_locked"], 1.8e6, 0.035, 1e-3, "adaptor")

@@ -196,7 +196,7 @@ def test_pll_identity_output_filter_and_first_sample():
     out, lk = p.apply(np.ones(4, np.complex64))
     assert out[0] == 0.0 and lk[0] == 0  # value starts at 0+0i, so c = 0 (pll.rs:57-58,71)
     nph, val = p.state()
-    assert 0 <= nph < 1 and abs(abs(val) - 1.0) < 1e-6
+    assert abs(nph) < 1 and abs(abs(val) - 1.0) < 1e-6
 
 
 # ---- a5/a6 resampler (own spec; parity with libsamplerate UNPINNED) -------------------------------

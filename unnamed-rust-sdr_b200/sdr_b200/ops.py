@@ -31,9 +31,9 @@ def _ptr(x):
 def _stream_ptr(stream):
     if stream is None:
         return None
-    if hasattr(stream, "cuda_stream"):
-        return stream.cuda_stream
-    return int(stream)
+    h = stream.cuda_stream if hasattr(stream, "cuda_stream") else int(stream)
+    # NULL means "create your own stream" in the C ABI; the legacy default stream is cudaStreamLegacy (0x1)
+    return h if h else 1
 
 
 def device_count():
