@@ -1,0 +1,165 @@
+// host_mirror_test.cpp -- the reference-style usage of the C++ host mirror (host/sdr.hpp), checked against
+// the CPU oracle.  Reads like the reference's examples: source.filter(taps).decimate(r).resample(48e3),
+// fft::fft(signal.take(t)), PllDesign::new(...).design(rate).apply(v).
+// Built and run by tests/test_gpu_host_mirror.py (needs a GPU: there is no CPU fallback).
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "../../oracle/sdr_oracle.h"
+#include "../../unnamed-rust-sdr_b200/host/sdr.hpp"
+
+using namespace sdr;
+
+static int fails = 0;
+#define EXPECT(cond, ...)                          \
+    do {                                           \
+        if (!(cond)) {                             \
+            ++fails;                               \
+            printf("FAIL %s:%d: ", __FILE__, __LINE__); \
+            printf(__VA_ARGS__);                   \
+            printf("\n");                          \
+        }                                          \
+    } while (0)
+
+static uint64_t splitmix(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+static std::vector<float> lowpass(int n, double fc, double fs) {
+    std::vector<double> h(n);
+    double sum = 0;
+    for (int k = 0; k < n; ++k) {
+        double t = k - (n - 1) / 2.0, a = 2 * fc / fs;
+        double s = (t == 0) ? 1.0 : std::sin(M_PI * a * t) / (M_PI * a * t);
+        h[k] = a * s * (0.54 - 0.46 * std::cos(2 * M_PI * k / (n - 1)));
+        sum += h[k];
+    }
+    std::vector<float> o(n);
+    for (int k = 0; k < n; ++k) o[k] = (float)(h[k] / sum);
+    return o;
+}
+
+int main() {
+    // ---- rtl_tcp bytes -> filter(255 taps) -> decimate(240e3) -> resample(48e3)  (BASELINE config C3) ----
+    const size_t n = 120000;
+    std::vector<uint8_t> raw(2 * n);
+    for (size_t i = 0; i < 2 * n; ++i) raw[i] = (uint8_t)(splitmix(i ^ 0x5D12B200) >> 56);
+    std::vector<float> taps = lowpass(255, 100e3, 2.4e6);
+
+    auto src = signal::from_u8iq(2.4e6f, raw);
+    auto dec = signal::decimate(signal::filter(src, taps), 240e3f);
+    EXPECT(dec->rate() == 2.4e6f, "Decimate::rate() must report the upstream rate (adapters/mod.rs:38-40)");
+    std::vector<Complex> y = dec->collect(50000);
+    EXPECT(y.size() == n / 10, "decimated count %zu", y.size());
+
+    std::vector<float> x(2 * n), full(2 * n);
+    orc_unpack_u8iq(raw.data(), n, x.data());
+    std::vector<double> truth(2 * n);
+    orc_fir_f64(taps.data(), taps.size(), 0, ORC_KIND_C64, x.data(), n, truth.data());
+    double maxy = 0, maxe = 0;
+    for (size_t j = 0; j < y.size(); ++j) {
+        const size_t i = (j + 1) * 10 - 1;
+        maxy = std::fmax(maxy, std::hypot(truth[2 * i], truth[2 * i + 1]));
+        maxe = std::fmax(maxe, std::hypot(y[j].real() - truth[2 * i], y[j].imag() - truth[2 * i + 1]));
+    }
+    EXPECT(maxe / maxy < 1e-5, "FIR rel err %g", maxe / maxy);
+
+    // relabel the rate as the harness must, then resample
+    auto res = signal::resample_with(signal::from_iter(240e3f, y), resample::ConverterType::SincFastest, 48e3f);
+    std::vector<Complex> z = res->collect();
+    std::vector<float> zr(2 * (y.size() / 5 + 8192));
+    const size_t nz = orc_resample_signal(reinterpret_cast<const float *>(y.data()), y.size(), 2, ORC_SRC_SINC_FASTEST,
+                                          (double)48e3f / (double)240e3f, zr.data(), zr.size() / 2);
+    EXPECT(z.size() == nz, "resampled count %zu vs oracle %zu", z.size(), nz);
+    double rmax = 0;
+    for (size_t i = 0; i < std::min(z.size(), nz); ++i)
+        rmax = std::fmax(rmax, std::hypot(z[i].real() - zr[2 * i], z[i].imag() - zr[2 * i + 1]));
+    EXPECT(rmax < 2e-7, "resample max abs diff %g", rmax);
+
+    // ---- SampleRate contract (resample.rs:33-99) ----
+    {
+        resample::SampleRate<Complex> sr(resample::ConverterType::Linear);
+        EXPECT(sr.channels() == 2, "channels");
+        std::vector<Complex> in(100, Complex(1, -1)), out;
+        out.reserve(4096);
+        size_t used = sr.process(0.5, in, out);
+        EXPECT(used == 100 && out.size() == 50, "linear used %zu out %zu", used, out.size());
+        bool threw = false;
+        try { sr.process(1e-9, in, out); } catch (const resample::Error &e) { threw = (e.code == 6); }
+        EXPECT(threw, "BadSrcRatio expected");
+        auto c = sr.try_clone();
+        sr.reset();
+    }
+
+    // ---- fft::fft(signal.take(t))  (examples/live.rs:31-38 uses 1000 points) ----
+    {
+        std::vector<Complex> s(5000);
+        for (size_t i = 0; i < s.size(); ++i) s[i] = Complex(std::cos(2 * M_PI * 0.05 * i), std::sin(2 * M_PI * 0.05 * i));
+        auto spec = fft::fft(signal::take(signal::from_iter(300000.0f, s), 1000.0f / 300000.0f));
+        EXPECT(spec.size() == 1000, "fft len %zu", spec.size());
+        std::vector<float> lab(1000), vals(2000);
+        orc_fft_shifted(reinterpret_cast<const float *>(s.data()), 1000, 300000.0f, lab.data(), vals.data());
+        double e = 0, m = 0;
+        for (size_t i = 0; i < 1000; ++i) {
+            EXPECT(spec[i].first == lab[i], "label %zu", i);
+            e = std::fmax(e, std::hypot(spec[i].second.real() - vals[2 * i], spec[i].second.imag() - vals[2 * i + 1]));
+            m = std::fmax(m, std::hypot(vals[2 * i], vals[2 * i + 1]));
+        }
+        EXPECT(e / m < 1e-4, "fft rel err %g", e / m);
+        std::vector<float> r(14400);
+        for (size_t i = 0; i < r.size(); ++i) r[i] = (float)std::sin(2 * M_PI * 0.01 * i);
+        auto rs = fft::rfft(signal::from_iter(144000.0f, r));  // examples/fft.rs:64,78
+        EXPECT(rs.size() == 7200 && rs[0].first == 0.0f, "rfft len %zu", rs.size());
+    }
+
+    // ---- PllDesign::new(...).design(rate).apply(v)  (examples/pll.rs:8-18) ----
+    {
+        std::vector<float> fr(1890), sw(2 * 1890);
+        const size_t ns = orc_freq_sweep(1800000.0f, 20000.0f, 1, -200000.0f, 200000.0f, fr.data(), sw.data(), 1890);
+        EXPECT(ns == 1890, "sweep len");
+        filter::PllDesign d(0.0f, 0.035f, filter::BiquadD::LowPass(80000.0f, 0.7f), filter::BiquadD::LowPass(20000.0f, 0.7f),
+                            filter::BiquadD::LowPass(20000.0f, 0.7f));
+        filter::Pll pll = d.design(1800000.0f);
+        std::vector<std::optional<float>> out;
+        pll.process(reinterpret_cast<const Complex *>(sw.data()), ns, out);
+        orc_pll_design_t od{0.0f, 0.035f, ORC_BQ_LOWPASS, 80000.0f, 0.7f, ORC_BQ_LOWPASS, 20000.0f, 0.7f, ORC_BQ_LOWPASS, 20000.0f, 0.7f};
+        orc_pll_t *op = orc_pll_new(&od, 1800000.0f);
+        std::vector<float> ro(ns);
+        std::vector<uint8_t> rl(ns);
+        orc_pll_apply(op, sw.data(), ns, ro.data(), rl.data());
+        orc_pll_free(op);
+        size_t mism = 0;
+        double e = 0;
+        for (size_t i = 0; i < ns; ++i) {
+            if ((bool)out[i] != (bool)rl[i]) { ++mism; continue; }
+            if (out[i]) e = std::fmax(e, std::fabs(*out[i] - ro[i]));
+        }
+        EXPECT(mism <= 3 && e < 1e-3 * 1.8e6 * 0.035 * M_PI, "pll mismatches %zu err %g", mism, e);
+        EXPECT(std::fabs(std::abs(pll.value()) - 1.0f) < 1e-6, "pll.value on the unit circle");
+    }
+
+    // ---- Fir::apply per sample == block (filter/mod.rs:23-26) and clone keeps state ----
+    {
+        std::vector<float> t8 = lowpass(8, 0.2, 1.0);
+        filter::Fir<float, Complex> f(t8, 1, false, SDR_FIR_STRICT_ORDER);
+        orc_fir_t *of = orc_fir_new(t8.data(), 8, 0, ORC_KIND_C64);
+        for (int i = 0; i < 20; ++i) {
+            Complex v((float)i, (float)-i), w;
+            Complex g = f.apply(v);
+            orc_fir_apply(of, reinterpret_cast<const float *>(&v), 1, reinterpret_cast<float *>(&w));
+            EXPECT(g == w, "Fir::apply sample %d", i);
+        }
+        filter::Fir<float, Complex> f2(f);
+        Complex v(1, 2);
+        EXPECT(f.apply(v) == f2.apply(v), "clone state");
+        orc_fir_free(of);
+    }
+
+    printf(fails ? "HOST MIRROR: %d failure(s)\n" : "HOST MIRROR OK\n", fails);
+    return fails ? 1 : 0;
+}

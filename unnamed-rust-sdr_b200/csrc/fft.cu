@@ -178,6 +178,149 @@ fft_cta_kernel(FftArgs a) {
     }
 }
 
+// ---- n = 1024, the headline size: one warp per transform, 32 points per lane -----------------
+// 1024 = 32 x 32: two radix-32 passes held entirely in registers and ONE exchange through
+// warp-private shared memory, so the only synchronisation is __syncwarp().  Persistent warps loop
+// over transforms; for u8 IQ the next transform's 2 KB of bytes is prefetched with cp.async while
+// the current one is computed, so HBM latency is hidden with only 16 warps per SM.  The pass-2
+// twiddles W_1024^{q*lane} live in a [31][32] shared table built once per CTA from the host f64
+// table (exact values, conflict-free reads).  When 1/sqrt(N) is a power of two (N = 4^k) the
+// normalisation is folded into the unpack constants (u8) or the twiddle table (c64): scaling by a
+// power of two commutes with every rounding, so the result is bit-identical to scaling afterwards.
+// cos / sin of pi*r/16, r = 0..8 (first quadrant); W32^r = (cos, -sin) extended by symmetry
+__host__ __device__ constexpr float w32_q(int r) {
+    return r == 0 ? 1.0f : r == 1 ? 0.98078528040323044913f : r == 2 ? 0.92387953251128675613f
+         : r == 3 ? 0.83146961230254523708f : r == 4 ? 0.70710678118654752440f : r == 5 ? 0.55557023301960222474f
+         : r == 6 ? 0.38268343236508977173f : r == 7 ? 0.19509032201612826785f : 0.0f;
+}
+__host__ __device__ constexpr float w32_cos(int r) { return r <= 8 ? w32_q(r) : -w32_q(16 - r); }
+__host__ __device__ constexpr float w32_sin(int r) { return r <= 8 ? w32_q(8 - r) : w32_q(r - 8); }
+
+// 32-point forward DFT, v (natural order) -> w (natural order).  n = c + 2a: two 16-point DFTs over the even
+// and odd inputs, then X[r] = U0[r] + W32^r U1[r], X[r+16] = U0[r] - W32^r U1[r].
+__device__ __forceinline__ void dft32(float2 (&v)[32], float2 (&w)[32]) {
+    dft<16, 2>(v);
+    dft<16, 2>(v + 1);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const float2 u0 = v[2 * r], u1 = v[2 * r + 1];
+        float2 t;
+        if (r == 0) t = u1;
+        else if (r == 8) t = mul_mi(u1);
+        else if (r == 4) t = make_float2((u1.x + u1.y) * C_SQRT1_2, (u1.y - u1.x) * C_SQRT1_2);
+        else if (r == 12) t = make_float2((u1.y - u1.x) * C_SQRT1_2, -(u1.x + u1.y) * C_SQRT1_2);
+        else t = cmul(u1, make_float2(w32_cos(r), -w32_sin(r)));
+        w[r] = cadd(u0, t);
+        w[r + 16] = csub(u0, t);
+    }
+}
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+constexpr int W1K_WARPS = 8;  // 8 warps share one twiddle table; 2 CTAs (16 warps, ~214 KB smem) per SM
+constexpr int W1K_XCH = 33 * 32;  // padded exchange, float2 per warp
+__host__ __device__ constexpr size_t w1k_smem(int fmt) {
+    return (size_t)(31 * 32 + W1K_WARPS * W1K_XCH) * sizeof(float2) + (fmt == SDR_FMT_U8IQ ? W1K_WARPS * 4096 : 0);
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(W1K_WARPS * 32, 2) fft1024_warp_kernel(FftArgs a) {
+    constexpr int N = 1024;
+    extern __shared__ float4 smem4[];
+    float2 *tw_s = reinterpret_cast<float2 *>(smem4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float2 *xch = tw_s + 31 * 32 + warp * W1K_XCH;
+    unsigned char *raw = reinterpret_cast<unsigned char *>(tw_s + 31 * 32 + W1K_WARPS * W1K_XCH) + warp * 4096;
+    const bool shift = (a.flags & SDR_FFT_SHIFT) != 0;
+    const bool norm = (a.flags & SDR_FFT_NORM) != 0;
+    const float fold = norm ? a.norm : 1.0f;  // 1/32: exact power of two
+    for (int idx = tid; idx < 31 * 32; idx += W1K_WARPS * 32) {
+        const int q = idx / 32 + 1, l = idx % 32;
+        float2 t = __ldg(a.tw + q * l);
+        if (FMT != SDR_FMT_U8IQ) { t.x *= fold; t.y *= fold; }
+        tw_s[idx] = t;
+    }
+    __syncthreads();
+    const long long nwarps = (long long)gridDim.x * W1K_WARPS;
+    long long b = (long long)blockIdx.x * W1K_WARPS + warp;
+    const float us = 0.0078125f * fold, uo = -65537.0f * fold;
+    const unsigned char *in8 = reinterpret_cast<const unsigned char *>(a.in);
+    int buf = 0;
+    if (FMT == SDR_FMT_U8IQ && b < a.batches) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) cp_async16(raw + (i * 32 + lane) * 16, in8 + b * 2048 + (i * 32 + lane) * 16);
+        cp_async_commit();
+    }
+    for (; b < a.batches; b += nwarps) {
+        float2 v[32], w[32];
+        if (FMT == SDR_FMT_U8IQ) {
+            const long long nb = b + nwarps;
+            if (nb < a.batches) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    cp_async16(raw + (buf ^ 1) * 2048 + (i * 32 + lane) * 16, in8 + nb * 2048 + (i * 32 + lane) * 16);
+                cp_async_commit();
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const unsigned short *r16 = reinterpret_cast<const unsigned short *>(raw + buf * 2048);
+#pragma unroll
+            for (int e = 0; e < 32; ++e) {
+                const unsigned h = r16[lane + 32 * e];
+                const unsigned mi = __byte_perm(h, 0x4B000000u, 0x7540u), mq = __byte_perm(h, 0x4B000000u, 0x7541u);
+                v[e] = make_float2(__fmaf_rn(__uint_as_float(mi), us, uo), __fmaf_rn(__uint_as_float(mq), us, uo));
+            }
+            buf ^= 1;
+        } else {
+            const float2 *src = reinterpret_cast<const float2 *>(a.in) + b * N + lane;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = __ldg(src + 32 * e);
+        }
+        dft32(v, w);
+#pragma unroll
+        for (int s = 0; s < 32; ++s) xch[33 * lane + s] = w[s];
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = xch[lane + 33 * e];
+#pragma unroll
+        for (int q = 1; q < 32; ++q) v[q] = cmul(v[q], tw_s[(q - 1) * 32 + lane]);
+        if (FMT != SDR_FMT_U8IQ && norm) { v[0].x *= fold; v[0].y *= fold; }
+        dft32(v, w);
+        float2 *dst = a.out + b * N + lane;
+#pragma unroll
+        for (int s = 0; s < 32; ++s) dst[32 * (shift ? (s ^ 16) : s)] = w[s];
+        __syncwarp();
+    }
+}
+
+template <int FMT>
+int launch_w1k(const FftArgs &a, cudaStream_t st) {
+    const size_t smem = w1k_smem(FMT);
+    auto kern = fft1024_warp_kernel<FMT>;
+    static bool configured = false;
+    static int sms = 148;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        configured = true;
+    }
+    long long ctas = (a.batches + W1K_WARPS - 1) / W1K_WARPS;
+    if (ctas > (long long)sms * 2) ctas = (long long)sms * 2;
+    kern<<<(unsigned)ctas, W1K_WARPS * 32, smem, st>>>(a);
+    count_launch();
+    return launch_status();
+}
+
 // ---- n = 2^15, 2^16: four-step, tile of 16 columns per CTA --------------------------------
 // STEP 0: view x as [256][M] (M = n/256); 256-point FFT down each column c; result row-major
 //         scratch[256*c + k2] (in the output buffer).
@@ -306,7 +449,11 @@ int launch_fmt(const FftArgs &a, cudaStream_t st) {
         case 7: return launch_cta<7, FMT>(a, st);
         case 8: return launch_cta<8, FMT>(a, st);
         case 9: return launch_cta<9, FMT>(a, st);
-        case 10: return launch_cta<10, FMT>(a, st);
+        case 10:
+            // 1/sqrt(1024) = 2^-5 folds exactly; the warp kernel handles U8IQ and C64 without RFFT
+            if (FMT != SDR_FMT_F32 && !(a.flags & SDR_FFT_RFFT) && (((uintptr_t)a.in) & 15) == 0)
+                return launch_w1k<FMT>(a, st);
+            return launch_cta<10, FMT>(a, st);
         case 11: return launch_cta<11, FMT>(a, st);
         case 12: return launch_cta<12, FMT>(a, st);
         case 13: return launch_cta<13, FMT>(a, st);
