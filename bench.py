@@ -131,7 +131,7 @@ def wl_fir_u8(torch, sdr, dev, K=64, D=1, log2_samples=26, complex_taps=False):
         taps = gen.complex_bandpass_taps(K, 200e3, 100e3, fs)
     g = torch.Generator(device=dev).manual_seed(0x5D12B200 + 1)
     raw = torch.randint(0, 256, (2 * samples,), dtype=torch.uint8, device=dev, generator=g)
-    n_out = samples // D
+    n_out = samples // D + 1  # the decimation phase carries over between steps
     out = torch.empty(n_out, dtype=torch.complex64, device=dev)
     fir = sdr.Fir(taps, "u8iq", decimation=D, device=dev.index, stream=torch.cuda.current_stream(dev))
 
@@ -191,7 +191,7 @@ def wl_fft_c64(torch, sdr, dev, logn=12, log2_samples=27):
                 kernel="fft", desc="batched %d-pt c64 FFT, %d transforms" % (n, batches))
 
 
-def wl_channelizer(torch, sdr, dev, n_ch=128, log2_n=16):
+def wl_channelizer(torch, sdr, dev, n_ch=128, log2_n=16, fast=False):
     import gen
     n = 1 << log2_n
     taps = gen.lowpass_taps(255, 100e3, 1.8e6)
@@ -201,7 +201,7 @@ def wl_channelizer(torch, sdr, dev, n_ch=128, log2_n=16):
     x.view(torch.float32).uniform_(-1, 1)
     out = torch.empty((n_ch, n), dtype=torch.float32, device=dev)
     lk = torch.empty((n_ch, n), dtype=torch.uint8, device=dev)
-    ch = sdr.Channelizer(taps, design, n_ch, 1.8e6, device=dev.index, stream=torch.cuda.current_stream(dev))
+    ch = sdr.Channelizer(taps, design, n_ch, 1.8e6, fast_math=fast, device=dev.index, stream=torch.cuda.current_stream(dev))
 
     def step():
         ch.process_dev(x, n, out, lk, n, n)
@@ -216,7 +216,7 @@ def wl_channelizer(torch, sdr, dev, n_ch=128, log2_n=16):
         O.channelizer_mt(xs, taps, od, 1.8e6, threads)
         return time.perf_counter() - t0
 
-    return dict(name="c4_channelizer_%dch_2p%d" % (n_ch, log2_n), units=n_ch * n, bytes_per_unit=12.125, step=step,
+    return dict(name="c4_channelizer_%dch_2p%d%s" % (n_ch, log2_n, "_fastmath" if fast else ""), units=n_ch * n, bytes_per_unit=12.125, step=step,
                 e2e_setup=None, e2e_step=None, h2d=8 * n_ch * n, d2h=5 * n_ch * n, cpu=cpu, dtype="f32",
                 kernel="fir_rb_kernel+pll_kernel", desc="%d channels x (255-tap FIR + PLL)" % n_ch)
 
@@ -236,6 +236,12 @@ def make_workload(name, torch, sdr, dev):
         return wl_fir_u8(torch, sdr, dev, 255, 1)
     if name == "c4":
         return wl_channelizer(torch, sdr, dev)
+    if name == "c4fast":
+        return wl_channelizer(torch, sdr, dev, fast=True)
+    if name == "c4_1024":
+        return wl_channelizer(torch, sdr, dev, n_ch=1024, log2_n=14)
+    if name == "c4_1024fast":
+        return wl_channelizer(torch, sdr, dev, n_ch=1024, log2_n=14, fast=True)
     if name.startswith("c5_"):
         return wl_fft_c64(torch, sdr, dev, int(name[3:]))
     raise SystemExit("unknown workload " + name)

@@ -46,6 +46,56 @@ int copy2d(void *dst, size_t dpitch, const void *src, size_t spitch, size_t widt
     return cuda_status(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, st));
 }
 
+// Double-buffered host<->device pipeline for the host-pointer entry points: chunk c is uploaded on `up`,
+// computed on the handle's stream and downloaded on `down`, so H2D(c+1), kernel(c) and D2H(c-1) overlap
+// (PCIe is full duplex).  Events order buffer reuse; nothing here touches sample values.
+struct HostPipe {
+    cudaStream_t up = nullptr, down = nullptr;
+    cudaEvent_t e_up[2] = {nullptr, nullptr}, e_k[2] = {nullptr, nullptr}, e_down[2] = {nullptr, nullptr};
+    bool ready = false;
+    int init() {
+        if (ready) return SDR_OK;
+        SDR_CUDA_TRY(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+        SDR_CUDA_TRY(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            SDR_CUDA_TRY(cudaEventCreateWithFlags(&e_up[i], cudaEventDisableTiming));
+            SDR_CUDA_TRY(cudaEventCreateWithFlags(&e_k[i], cudaEventDisableTiming));
+            SDR_CUDA_TRY(cudaEventCreateWithFlags(&e_down[i], cudaEventDisableTiming));
+        }
+        ready = true;
+        return SDR_OK;
+    }
+    void release() {
+        if (up) cudaStreamDestroy(up);
+        if (down) cudaStreamDestroy(down);
+        for (int i = 0; i < 2; ++i) {
+            if (e_up[i]) cudaEventDestroy(e_up[i]);
+            if (e_k[i]) cudaEventDestroy(e_k[i]);
+            if (e_down[i]) cudaEventDestroy(e_down[i]);
+        }
+        up = down = nullptr;
+        ready = false;
+    }
+    // before uploading into buffer b: the kernel that last read it must be done
+    int begin_upload(int b) { return cuda_status(cudaStreamWaitEvent(up, e_k[b], 0)); }
+    int end_upload(int b) { return cuda_status(cudaEventRecord(e_up[b], up)); }
+    // before the kernel on `main` touches buffer b: its upload is done and the download that last read out[b] is done
+    int begin_compute(int b, cudaStream_t main) {
+        SDR_CUDA_TRY(cudaStreamWaitEvent(main, e_up[b], 0));
+        return cuda_status(cudaStreamWaitEvent(main, e_down[b], 0));
+    }
+    int end_compute(int b, cudaStream_t main) {
+        SDR_CUDA_TRY(cudaEventRecord(e_k[b], main));
+        return cuda_status(cudaStreamWaitEvent(down, e_k[b], 0));
+    }
+    int end_download(int b) { return cuda_status(cudaEventRecord(e_down[b], down)); }
+    int drain(cudaStream_t main) {
+        SDR_CUDA_TRY(cudaStreamSynchronize(down));
+        SDR_CUDA_TRY(cudaStreamSynchronize(up));
+        return cuda_status(cudaStreamSynchronize(main));
+    }
+};
+
 }  // namespace
 
 // ============================================================================================
@@ -138,10 +188,12 @@ struct sdr_fir {
     size_t hist_stride = 0;
     std::vector<float> taps;  // padded host copy
     float *d_taps = nullptr;
+    uint2 *d_tc_tables = nullptr;  // tensor-core Toeplitz tap fragments (u8 input, non-strict)
     void *d_hist[2] = {nullptr, nullptr};
     int cur = 0;
     size_t phase = 0;  // inputs already discarded in the current decimation group
-    DevBuf d_in, d_out;
+    DevBuf d_in, d_out, d_in2, d_out2;
+    HostPipe pipe;
     int last_path = 0;
 };
 
@@ -149,10 +201,14 @@ static void fir_free(sdr_fir *f) {
     if (!f) return;
     DeviceGuard g(f->dev);
     if (f->d_taps) cudaFree(f->d_taps);
+    if (f->d_tc_tables) cudaFree(f->d_tc_tables);
     for (int i = 0; i < 2; ++i)
         if (f->d_hist[i]) cudaFree(f->d_hist[i]);
     f->d_in.release();
     f->d_out.release();
+    f->d_in2.release();
+    f->d_out2.release();
+    f->pipe.release();
     f->stream.release();
     delete f;
 }
@@ -167,6 +223,13 @@ static int fir_alloc(sdr_fir *f, void *user_stream) {
     for (int i = 0; i < 2; ++i) SDR_CUDA_TRY(cudaMalloc(&f->d_hist[i], hbytes));
     rc = fir_fill_hist(f->d_hist[0], f->fmt, (long long)(f->n_ch * f->hist_stride), f->stream.s);
     if (rc) return rc;
+    if (f->fmt == SDR_FMT_U8IQ && !(f->flags & (SDR_FIR_STRICT_ORDER | SDR_FIR_NO_TENSOR)) && f->K <= 4096 && f->D <= 64) {
+        std::vector<uint2> tab;
+        fir_tc_build_tables(f->taps.data(), (int)f->K, f->taps_complex != 0, (int)f->D, tab);
+        SDR_CUDA_TRY(cudaMalloc(&f->d_tc_tables, tab.size() * sizeof(uint2)));
+        SDR_CUDA_TRY(cudaMemcpyAsync(f->d_tc_tables, tab.data(), tab.size() * sizeof(uint2), cudaMemcpyHostToDevice, f->stream.s));
+        SDR_CUDA_TRY(cudaStreamSynchronize(f->stream.s));
+    }
     SDR_CUDA_TRY(cudaStreamSynchronize(f->stream.s));
     return SDR_OK;
 }
@@ -256,7 +319,12 @@ static int fir_run_dev(sdr_fir *f, const void *in, size_t n_in, size_t in_stride
     a.first = (long long)(f->D - 1 - f->phase);
     a.K = (int)f->K; a.Kp = (int)f->Kp; a.HL = (int)f->HL; a.D = (int)f->D; a.n_ch = (int)f->n_ch;
     const bool strict = (f->flags & SDR_FIR_STRICT_ORDER) != 0;
-    int rc = fir_launch(a, f->fmt, f->taps_complex != 0, strict, f->stream.s, &f->last_path);
+    int rc = SDR_ERR_UNSUPPORTED;
+    if (f->d_tc_tables) {
+        rc = fir_tc_launch(a, f->taps_complex != 0, f->d_tc_tables, f->stream.s);
+        if (rc == SDR_OK) f->last_path = 3;
+    }
+    if (rc == SDR_ERR_UNSUPPORTED) rc = fir_launch(a, f->fmt, f->taps_complex != 0, strict, f->stream.s, &f->last_path);
     if (rc) return rc;
     rc = fir_hist_update(in, f->d_hist[f->cur], f->d_hist[f->cur ^ 1], f->fmt, (int)f->HL, (long long)n_in,
                          (long long)in_stride, (long long)f->hist_stride, (int)f->n_ch, f->stream.s);
@@ -300,20 +368,45 @@ extern "C" int sdr_fir_process(sdr_fir_t *f, const void *in, size_t n_in, size_t
     if (in_stride < n_in || out_stride < no) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(f->dev);
     const size_t es_in = elem_bytes(f->fmt), es_out = (f->fmt == SDR_FMT_F32) ? 4 : 8;
-    const size_t dstride_in = round_up(n_in, 8), dstride_out = round_up(std::max<size_t>(no, 1), 2);
-    int rc = f->d_in.reserve(f->n_ch * dstride_in * es_in);
-    if (!rc) rc = f->d_out.reserve(f->n_ch * dstride_out * es_out);
-    if (rc) return rc;
     cudaStream_t st = f->stream.s;
-    rc = copy2d(f->d_in.p, dstride_in * es_in, in, in_stride * es_in, n_in * es_in, f->n_ch, cudaMemcpyHostToDevice, st);
+    // chunks of ~32 MiB of input per channel-set, multiples of 2048*D samples so every chunk but the last keeps the
+    // fast kernel's alignment; H2D(c+1) / kernel(c) / D2H(c-1) overlap
+    size_t chunk = std::max<size_t>(1, ((size_t)32 << 20) / (es_in * f->n_ch));
+    chunk = std::max<size_t>(2048 * f->D, chunk / (2048 * f->D) * (2048 * f->D));
+    if (chunk > n_in) chunk = n_in;
+    const size_t out_per_chunk = chunk / f->D + 2;
+    const size_t ds_in = round_up(chunk, 8), ds_out = round_up(out_per_chunk, 2);
+    int rc = f->pipe.init();
+    DevBuf *bin[2] = {&f->d_in, &f->d_in2}, *bout[2] = {&f->d_out, &f->d_out2};
+    const int nbuf = (chunk < n_in) ? 2 : 1;
+    for (int i = 0; i < nbuf && !rc; ++i) {
+        rc = bin[i]->reserve(f->n_ch * ds_in * es_in);
+        if (!rc) rc = bout[i]->reserve(f->n_ch * ds_out * es_out);
+    }
     if (rc) return rc;
-    rc = fir_run_dev(f, f->d_in.p, n_in, dstride_in, f->d_out.p, dstride_out, no);
+    size_t done_in = 0, done_out = 0;
+    for (int c = 0; done_in < n_in; ++c) {
+        const int b = c & 1;
+        const size_t cnt = std::min(chunk, n_in - done_in);
+        const size_t cno = sdr_fir_output_count(f, cnt);
+        rc = f->pipe.begin_upload(b);
+        if (!rc) rc = copy2d(bin[b]->p, ds_in * es_in, (const char *)in + done_in * es_in, in_stride * es_in, cnt * es_in,
+                             f->n_ch, cudaMemcpyHostToDevice, f->pipe.up);
+        if (!rc) rc = f->pipe.end_upload(b);
+        if (!rc) rc = f->pipe.begin_compute(b, st);
+        if (!rc) rc = fir_run_dev(f, bin[b]->p, cnt, ds_in, bout[b]->p, ds_out, cno);
+        if (!rc) rc = f->pipe.end_compute(b, st);
+        if (!rc) rc = copy2d((char *)out + done_out * es_out, out_stride * es_out, bout[b]->p, ds_out * es_out, cno * es_out,
+                             f->n_ch, cudaMemcpyDeviceToHost, f->pipe.down);
+        if (!rc) rc = f->pipe.end_download(b);
+        if (rc) { f->pipe.drain(st); return rc; }
+        done_in += cnt;
+        done_out += cno;
+    }
+    rc = f->pipe.drain(st);
     if (rc) return rc;
-    rc = copy2d(out, out_stride * es_out, f->d_out.p, dstride_out * es_out, no * es_out, f->n_ch, cudaMemcpyDeviceToHost, st);
-    if (rc) return rc;
-    SDR_CUDA_TRY(cudaStreamSynchronize(st));
     if (n_used) *n_used = n_in;
-    if (n_out) *n_out = no;
+    if (n_out) *n_out = done_out;
     return SDR_OK;
 }
 
@@ -335,7 +428,8 @@ struct sdr_fft {
     int log_m = 0;
     float2 *d_chirp = nullptr, *d_bfft = nullptr;
     DevBuf d_a1, d_a2;
-    DevBuf d_in, d_out;
+    DevBuf d_in, d_out, d_in2, d_out2;
+    HostPipe pipe;
 };
 
 static void fft_free(sdr_fft *p) {
@@ -344,7 +438,8 @@ static void fft_free(sdr_fft *p) {
     if (p->d_tw) cudaFree(p->d_tw);
     if (p->d_chirp) cudaFree(p->d_chirp);
     if (p->d_bfft) cudaFree(p->d_bfft);
-    p->d_a1.release(); p->d_a2.release(); p->d_in.release(); p->d_out.release();
+    p->d_a1.release(); p->d_a2.release(); p->d_in.release(); p->d_out.release(); p->d_in2.release(); p->d_out2.release();
+    p->pipe.release();
     p->stream.release();
     delete p;
 }
@@ -490,18 +585,37 @@ extern "C" int sdr_fft_exec(sdr_fft_t *p, const void *in, size_t batches, float 
     if (batches == 0) return SDR_OK;
     if (!in || !out) return SDR_ERR_BAD_DATA_PTR;
     DeviceGuard g(p->dev);
-    const size_t in_bytes = batches * p->n * elem_bytes(p->fmt);
-    const size_t out_bytes = batches * sdr_fft_output_len(p) * sizeof(float2);
-    int rc = p->d_in.reserve(in_bytes);
-    if (!rc) rc = p->d_out.reserve(std::max(out_bytes, batches * p->n * sizeof(float2)));
-    if (rc) return rc;
+    const size_t es = elem_bytes(p->fmt), out_len = sdr_fft_output_len(p);
     cudaStream_t st = p->stream.s;
-    SDR_CUDA_TRY(cudaMemcpyAsync(p->d_in.p, in, in_bytes, cudaMemcpyHostToDevice, st));
-    rc = fft_run_dev(p, p->d_in.p, batches, (float *)p->d_out.p);
+    // chunks of ~32 MiB of input (at least one transform); H2D(c+1) / kernel(c) / D2H(c-1) overlap
+    size_t chunk = std::max<size_t>(1, ((size_t)32 << 20) / (p->n * es));
+    if (chunk > batches) chunk = batches;
+    int rc = p->pipe.init();
+    DevBuf *bin[2] = {&p->d_in, &p->d_in2}, *bout[2] = {&p->d_out, &p->d_out2};
+    const int nbuf = (chunk < batches) ? 2 : 1;
+    for (int i = 0; i < nbuf && !rc; ++i) {
+        rc = bin[i]->reserve(chunk * p->n * es);
+        if (!rc) rc = bout[i]->reserve(chunk * std::max(out_len, p->n) * sizeof(float2));
+    }
     if (rc) return rc;
-    SDR_CUDA_TRY(cudaMemcpyAsync(out, p->d_out.p, out_bytes, cudaMemcpyDeviceToHost, st));
-    SDR_CUDA_TRY(cudaStreamSynchronize(st));
-    return SDR_OK;
+    size_t done = 0;
+    for (int c = 0; done < batches; ++c) {
+        const int b = c & 1;
+        const size_t cnt = std::min(chunk, batches - done);
+        rc = p->pipe.begin_upload(b);
+        if (!rc) rc = cuda_status(cudaMemcpyAsync(bin[b]->p, (const char *)in + done * p->n * es, cnt * p->n * es,
+                                                  cudaMemcpyHostToDevice, p->pipe.up));
+        if (!rc) rc = p->pipe.end_upload(b);
+        if (!rc) rc = p->pipe.begin_compute(b, st);
+        if (!rc) rc = fft_run_dev(p, bin[b]->p, cnt, (float *)bout[b]->p);
+        if (!rc) rc = p->pipe.end_compute(b, st);
+        if (!rc) rc = cuda_status(cudaMemcpyAsync((char *)out + done * out_len * sizeof(float2), bout[b]->p,
+                                                  cnt * out_len * sizeof(float2), cudaMemcpyDeviceToHost, p->pipe.down));
+        if (!rc) rc = p->pipe.end_download(b);
+        if (rc) { p->pipe.drain(st); return rc; }
+        done += cnt;
+    }
+    return p->pipe.drain(st);
 }
 
 // fft.rs:14-24: fstep = rate / (len as f32); start = -(len as isize / 2); label = srci as f32 * fstep
