@@ -189,6 +189,7 @@ struct sdr_fir {
     std::vector<float> taps;  // padded host copy
     float *d_taps = nullptr;
     uint2 *d_tc_tables = nullptr;  // tensor-core Toeplitz tap fragments (u8 input, non-strict)
+    float tc_scale = 1.0f;
     void *d_hist[2] = {nullptr, nullptr};
     int cur = 0;
     size_t phase = 0;  // inputs already discarded in the current decimation group
@@ -225,7 +226,7 @@ static int fir_alloc(sdr_fir *f, void *user_stream) {
     if (rc) return rc;
     if (f->fmt == SDR_FMT_U8IQ && !(f->flags & (SDR_FIR_STRICT_ORDER | SDR_FIR_NO_TENSOR)) && f->K <= 4096 && f->D <= 64) {
         std::vector<uint2> tab;
-        fir_tc_build_tables(f->taps.data(), (int)f->K, f->taps_complex != 0, (int)f->D, tab);
+        f->tc_scale = fir_tc_build_tables(f->taps.data(), (int)f->K, f->taps_complex != 0, (int)f->D, tab);
         SDR_CUDA_TRY(cudaMalloc(&f->d_tc_tables, tab.size() * sizeof(uint2)));
         SDR_CUDA_TRY(cudaMemcpyAsync(f->d_tc_tables, tab.data(), tab.size() * sizeof(uint2), cudaMemcpyHostToDevice, f->stream.s));
         SDR_CUDA_TRY(cudaStreamSynchronize(f->stream.s));
@@ -321,7 +322,7 @@ static int fir_run_dev(sdr_fir *f, const void *in, size_t n_in, size_t in_stride
     const bool strict = (f->flags & SDR_FIR_STRICT_ORDER) != 0;
     int rc = SDR_ERR_UNSUPPORTED;
     if (f->d_tc_tables) {
-        rc = fir_tc_launch(a, f->taps_complex != 0, f->d_tc_tables, f->stream.s);
+        rc = fir_tc_launch(a, f->taps_complex != 0, f->d_tc_tables, f->tc_scale, f->stream.s);
         if (rc == SDR_OK) f->last_path = 3;
     }
     if (rc == SDR_ERR_UNSUPPORTED) rc = fir_launch(a, f->fmt, f->taps_complex != 0, strict, f->stream.s, &f->last_path);

@@ -30,10 +30,11 @@ int unpack_launch(const uint8_t *iq, size_t n, float *out, cudaStream_t st);
 }  // namespace sdr
 #include <vector>
 namespace sdr {
-int fir_tc_ksteps(int K, int D);
-void fir_tc_build_tables(const float *taps, int K, bool taps_complex, int D, std::vector<uint2> &out);
+int fir_tc_ksteps(int K, int D, bool taps_complex);
+// returns the exact power-of-two epilogue scale
+float fir_tc_build_tables(const float *taps, int K, bool taps_complex, int D, std::vector<uint2> &out);
 // SDR_ERR_UNSUPPORTED = the tensor path does not apply to this call (alignment / shared-memory budget)
-int fir_tc_launch(const FirArgs &a, bool taps_complex, const uint2 *d_tables, cudaStream_t st);
+int fir_tc_launch(const FirArgs &a, bool taps_complex, const uint2 *d_tables, float out_scale, cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------
 // FFT (fft.cu)

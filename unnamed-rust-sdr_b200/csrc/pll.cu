@@ -83,17 +83,26 @@ __device__ __forceinline__ Biquad1 make_bq(const float *c, int kind) {
     return b;
 }
 
-// one warp = 32 streams.  Tiles of 32 samples are staged through shared memory.
+__device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// One warp (= one CTA) owns 32 streams.  [32 streams x 32 samples] tiles are staged through shared memory: the
+// next tile streams in with cp.async (256-byte row segments) while the lanes step the current one, so the
+// sequential per-stream loop never waits on HBM; outputs leave as 128-byte row segments.
 template <bool FAST>
-__global__ void __launch_bounds__(64) pll_kernel(const float2 *__restrict__ in, long long n, long long in_stride,
-                                                  float *__restrict__ out, uint8_t *__restrict__ locked,
-                                                  long long out_stride, const PllParams *__restrict__ params,
-                                                  int params_shared, PllState *__restrict__ state, int n_streams) {
+__global__ void __launch_bounds__(32) pll_kernel(const float2 *__restrict__ in, long long n, long long in_stride,
+                                                 float *__restrict__ out, uint8_t *__restrict__ locked,
+                                                 long long out_stride, const PllParams *__restrict__ params,
+                                                 int params_shared, PllState *__restrict__ state, int n_streams) {
     __shared__ float2 s_in[2][32][PLL_CHUNK + 1];
-    __shared__ float s_out[2][32][PLL_CHUNK + 1];
-    __shared__ uint8_t s_lk[2][32][PLL_CHUNK + 4];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int stream0 = (blockIdx.x * 2 + warp) * 32;
+    __shared__ float s_out[32][PLL_CHUNK + 1];
+    __shared__ uint8_t s_lk[32][PLL_CHUNK + 4];
+    const int lane = threadIdx.x;
+    const int stream0 = blockIdx.x * 32;
     if (stream0 >= n_streams) return;
     const int my = stream0 + lane;
     const bool live = my < n_streams;
@@ -101,29 +110,50 @@ __global__ void __launch_bounds__(64) pll_kernel(const float2 *__restrict__ in, 
     PllState st = state[live ? my : stream0];
     const Biquad1 lf = make_bq(p.lc, p.lk), of = make_bq(p.oc, p.ok), kf = make_bq(p.kc, p.kk);
     const int nrows = min(32, n_streams - stream0);
+    const long long ntiles = (n + PLL_CHUNK - 1) / PLL_CHUNK;
 
-    for (long long base = 0; base < n; base += PLL_CHUNK) {
+    auto issue = [&](long long tile, int buf) {
+        const long long base = tile * PLL_CHUNK;
         const int cnt = (int)min((long long)PLL_CHUNK, n - base);
-        // stage in: row r of the tile = stream stream0+r, 32 consecutive samples (256 B)
-        for (int r = 0; r < nrows; ++r)
-            if (lane < cnt) s_in[warp][r][lane] = in[(long long)(stream0 + r) * in_stride + base + lane];
+        if (lane < cnt) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+                if (r < nrows) cp_async8(&s_in[buf][r][lane], in + (long long)(stream0 + r) * in_stride + base + lane);
+        }
+        cp_async_commit();
+    };
+
+    issue(0, 0);
+    for (long long tile = 0; tile < ntiles; ++tile) {
+        const int buf = (int)(tile & 1);
+        const long long base = tile * PLL_CHUNK;
+        const int cnt = (int)min((long long)PLL_CHUNK, n - base);
+        if (tile + 1 < ntiles) {
+            issue(tile + 1, buf ^ 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
         __syncwarp();
         if (live) {
             for (int i = 0; i < cnt; ++i) {
-                const float2 x = s_in[warp][lane][i];
+                const float2 x = s_in[buf][lane][i];
                 float o;
                 uint8_t l;
                 pll_step<FAST>(p, lf, of, kf, st, x.x, x.y, o, l);
-                s_out[warp][lane][i] = o;
-                s_lk[warp][lane][i] = l;
+                s_out[lane][i] = o;
+                s_lk[lane][i] = l;
             }
         }
         __syncwarp();
-        for (int r = 0; r < nrows; ++r)
-            if (lane < cnt) {
-                out[(long long)(stream0 + r) * out_stride + base + lane] = s_out[warp][r][lane];
-                locked[(long long)(stream0 + r) * out_stride + base + lane] = s_lk[warp][r][lane];
-            }
+        if (lane < cnt) {
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r)
+                if (r < nrows) {
+                    out[(long long)(stream0 + r) * out_stride + base + lane] = s_out[r][lane];
+                    locked[(long long)(stream0 + r) * out_stride + base + lane] = s_lk[r][lane];
+                }
+        }
         __syncwarp();
     }
     if (live) state[my] = st;
@@ -135,11 +165,11 @@ int pll_launch(const float2 *in, long long n, long long in_stride, float *out, u
                const PllParams *params, int params_shared, PllState *state, int n_streams, bool fast_math,
                cudaStream_t st) {
     if (n <= 0 || n_streams <= 0) return SDR_OK;
-    const unsigned grid = (unsigned)((n_streams + 63) / 64);
+    const unsigned grid = (unsigned)((n_streams + 31) / 32);
     if (fast_math)
-        pll_kernel<true><<<grid, 64, 0, st>>>(in, n, in_stride, out, locked, out_stride, params, params_shared, state, n_streams);
+        pll_kernel<true><<<grid, 32, 0, st>>>(in, n, in_stride, out, locked, out_stride, params, params_shared, state, n_streams);
     else
-        pll_kernel<false><<<grid, 64, 0, st>>>(in, n, in_stride, out, locked, out_stride, params, params_shared, state, n_streams);
+        pll_kernel<false><<<grid, 32, 0, st>>>(in, n, in_stride, out, locked, out_stride, params, params_shared, state, n_streams);
     count_launch();
     return launch_status();
 }
