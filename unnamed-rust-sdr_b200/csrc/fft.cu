@@ -321,6 +321,156 @@ int launch_w1k(const FftArgs &a, cudaStream_t st) {
     return launch_status();
 }
 
+// ---- n = 256 .. 8192 (other than 1024): persistent CTA, registers + one shared exchange per pass ------------
+// Same Stockham passes as fft_cta_kernel, without its staging round trips: the first pass loads straight from
+// global memory into registers (element t + e*TC: coalesced), the last pass stores straight from registers, middle
+// passes exchange through padded shared memory.  Twiddles never touch global memory in the loop: middle passes read
+// per-pass shared tables [q][k] (conflict free), the last pass keeps its (R-1)*16/R per-thread twiddles in
+// registers (a thread sees the same k for every transform because the CTA is persistent).  Threads of one
+// transform synchronise with a named barrier (or __syncwarp when a transform fits in a warp), so the transforms
+// sharing a CTA drift freely.
+template <int TC>
+__device__ __forceinline__ void group_sync(int group) {
+    if (TC <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(TC));
+}
+
+template <int LOGN>
+struct Reg2Plan {
+    static constexpr int N = 1 << LOGN, TC = N / 16;
+    static constexpr int THREADS = TC > 256 ? TC : 256;
+    static constexpr int SEQ = THREADS / TC;
+    static constexpr int NP = (LOGN + 3) / 4;                 // passes
+    static constexpr int RLAST = 1 << (LOGN - 4 * (NP - 1));  // radix of the last pass (16 if LOGN % 4 == 0)
+    static constexpr int NBLAST = 16 / RLAST;
+    // shared twiddle tables of the middle passes (pass j, 1 <= j <= NP-2): 15 * 16^j entries each
+    static constexpr int tab_entries() {
+        int e = 0, p = 16;
+        for (int j = 1; j <= NP - 2; ++j) { e += 15 * p; p *= 16; }
+        return e;
+    }
+    static constexpr size_t smem_bytes() { return ((size_t)SEQ * padlen(N) + tab_entries()) * sizeof(float2); }
+};
+
+// middle pass j (sub-size p = 16^j, radix 16): shared -> registers -> shared
+template <int LOGN, int PLOG>
+__device__ __forceinline__ void reg2_middle(float2 *sx, const float2 *tab, int t, int group) {
+    constexpr int N = 1 << LOGN, TC = N / 16, p = 1 << PLOG;
+    float2 v[16];
+#pragma unroll
+    for (int e = 0; e < 16; ++e) v[e] = sx[pad(t + e * TC)];
+    const int k = t & (p - 1);
+#pragma unroll
+    for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tab[(q - 1) * p + k]);
+    dft<16, 1>(v);
+    group_sync<TC>(group);
+    const int base = (t - k) * 16 + k;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) sx[pad(base + q * p)] = v[q];
+    group_sync<TC>(group);
+}
+
+template <int LOGN, int FMT>
+__global__ void __launch_bounds__(Reg2Plan<LOGN>::THREADS, (Reg2Plan<LOGN>::THREADS <= 256) ? 2 : 1)
+fft_reg2_kernel(FftArgs a) {
+    using PL = Reg2Plan<LOGN>;
+    constexpr int N = PL::N, TC = PL::TC, THREADS = PL::THREADS, SEQ = PL::SEQ, NP = PL::NP;
+    constexpr int RL = PL::RLAST, NBL = PL::NBLAST;
+    extern __shared__ float4 smem4[];
+    float2 *sm = reinterpret_cast<float2 *>(smem4);
+    float2 *tabs = sm + SEQ * padlen(N);
+    const int tid = threadIdx.x, group = tid / TC, t = tid % TC;
+    float2 *sx = sm + group * padlen(N);
+
+    // middle-pass tables: tab_j[(q-1)*p + k] = W_{16p}^{q k} = W_N^{q k N/(16p)}
+    {
+        int off = 0, p = 16;
+#pragma unroll
+        for (int j = 1; j <= NP - 2; ++j) {
+            for (int idx = tid; idx < 15 * p; idx += THREADS) {
+                const int q = idx / p + 1, k = idx % p;
+                tabs[off + idx] = __ldg(a.tw + (long long)q * k * (N / (16 * p)));
+            }
+            off += 15 * p;
+            p *= 16;
+        }
+    }
+    // last-pass twiddles of this thread: butterfly vi has k = t + vi*TC, element q gets W_N^{q k}
+    const bool norm = (a.flags & SDR_FFT_NORM) != 0;
+    float2 twl[NBL][RL - 1];
+#pragma unroll
+    for (int vi = 0; vi < NBL; ++vi)
+#pragma unroll
+        for (int q = 1; q < RL; ++q) twl[vi][q - 1] = __ldg(a.tw + (long long)q * (t + vi * TC));
+    __syncthreads();
+
+    const bool shift = (a.flags & SDR_FFT_SHIFT) != 0 && !(a.flags & SDR_FFT_RFFT);
+    const int out_len = (a.flags & SDR_FFT_RFFT) ? N - N / 2 : N;
+    for (long long b0 = (long long)blockIdx.x * SEQ; b0 < a.batches; b0 += (long long)gridDim.x * SEQ) {
+        const long long b = b0 + group;
+        const bool live = b < a.batches;
+        float2 v[16];
+        // ---- pass 0: global -> registers, radix 16, no twiddles ----
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = live ? load_elem<FMT>(a.in, b * N + t + e * TC) : make_float2(0.f, 0.f);
+        dft<16, 1>(v);
+        if (NP == 1) {
+            // (N == 16 is not dispatched here)
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) sx[pad(16 * t + q)] = v[q];
+        group_sync<TC>(group);
+        // ---- middle passes ----
+        if (NP >= 3) reg2_middle<LOGN, 4>(sx, tabs, t, group);
+        if (NP >= 4) reg2_middle<LOGN, 8>(sx, tabs + 15 * 16, t, group);
+        // ---- last pass: shared -> registers, per-thread twiddles, registers -> global ----
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = sx[pad(t + e * TC)];
+#pragma unroll
+        for (int vi = 0; vi < NBL; ++vi)
+#pragma unroll
+            for (int q = 1; q < RL; ++q) v[vi + q * NBL] = cmul(v[vi + q * NBL], twl[vi][q - 1]);
+#pragma unroll
+        for (int vi = 0; vi < NBL; ++vi) dft<RL, NBL>(v + vi);
+        if (live) {
+            float2 *dst = a.out + b * out_len;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) {
+                // register e = vi + q*NBL holds bin (t + vi*TC) + q*(N/RL) = t + e*TC
+                int k = t + e * TC;
+                if (shift) k = (k + N / 2) & (N - 1);
+                float2 o = v[e];
+                if (norm) { o.x *= a.norm; o.y *= a.norm; }
+                if (k < out_len) dst[k] = o;
+            }
+        }
+        group_sync<TC>(group);  // the exchange buffer is rewritten by the next transform
+    }
+}
+
+template <int LOGN, int FMT>
+int launch_reg2(const FftArgs &a, cudaStream_t st) {
+    using PL = Reg2Plan<LOGN>;
+    const size_t smem = PL::smem_bytes();
+    auto kern = fft_reg2_kernel<LOGN, FMT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PL::THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    long long ctas = (a.batches + PL::SEQ - 1) / PL::SEQ;
+    if (ctas > (long long)sms * per_sm) ctas = (long long)sms * per_sm;
+    kern<<<(unsigned)ctas, PL::THREADS, smem, st>>>(a);
+    count_launch();
+    return launch_status();
+}
+
 // ---- n = 2^15, 2^16: four-step, tile of 16 columns per CTA --------------------------------
 // STEP 0: view x as [256][M] (M = n/256); 256-point FFT down each column c; result row-major
 //         scratch[256*c + k2] (in the output buffer).
@@ -447,16 +597,16 @@ int launch_fmt(const FftArgs &a, cudaStream_t st) {
         case 5: return launch_cta<5, FMT>(a, st);
         case 6: return launch_cta<6, FMT>(a, st);
         case 7: return launch_cta<7, FMT>(a, st);
-        case 8: return launch_cta<8, FMT>(a, st);
-        case 9: return launch_cta<9, FMT>(a, st);
+        case 8: return launch_reg2<8, FMT>(a, st);
+        case 9: return launch_reg2<9, FMT>(a, st);
         case 10:
             // 1/sqrt(1024) = 2^-5 folds exactly; the warp kernel handles U8IQ and C64 without RFFT
             if (FMT != SDR_FMT_F32 && !(a.flags & SDR_FFT_RFFT) && (((uintptr_t)a.in) & 15) == 0)
                 return launch_w1k<FMT>(a, st);
             return launch_cta<10, FMT>(a, st);
-        case 11: return launch_cta<11, FMT>(a, st);
-        case 12: return launch_cta<12, FMT>(a, st);
-        case 13: return launch_cta<13, FMT>(a, st);
+        case 11: return launch_reg2<11, FMT>(a, st);
+        case 12: return launch_reg2<12, FMT>(a, st);
+        case 13: return launch_reg2<13, FMT>(a, st);
         case 14: return launch_cta<14, FMT>(a, st);
         case 15:
         case 16: return launch_big<FMT>(a, st);
