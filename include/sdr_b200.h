@@ -79,7 +79,8 @@ int sdr_unpack_u8iq_dev(const uint8_t *iq, size_t n_samples, float *out_c64, int
  * stream in blocks of any size gives the same samples as one call.
  * ====================================================================================== */
 #define SDR_FIR_STRICT_ORDER 1u /* f32 mul then add, k ascending, no FMA: bit-identical to Fir::apply */
-#define SDR_FIR_NO_TENSOR 2u    /* never take the tensor-core path */
+#define SDR_FIR_NO_TENSOR 2u    /* never take a tensor-core path */
+#define SDR_FIR_NO_TCGEN05 4u   /* never take the tcgen05/TMEM path (the mma.sync Toeplitz path may still run) */
 
 typedef struct {
     const float *taps;   /* n_taps f32, or n_taps (re,im) pairs when taps_complex */
@@ -109,7 +110,7 @@ int sdr_fir_process(sdr_fir_t *, const void *in, size_t n_in, size_t in_stride, 
 int sdr_fir_process_dev(sdr_fir_t *, const void *in, size_t n_in, size_t in_stride, void *out,
                         size_t out_cap, size_t out_stride, size_t *n_used, size_t *n_out);
 /* which kernel family the last process call used: 0 none, 1 CUDA-core direct, 2 CUDA-core
- * strict-order, 3 tensor-core Toeplitz */
+ * strict-order, 3 tensor-core Toeplitz (mma.sync), 4 tensor-core Toeplitz (tcgen05 / TMEM, integer) */
 int sdr_fir_last_path(const sdr_fir_t *);
 
 /* Decimate::new's `wait` = (rate_in / rate_out).round() as usize in f32 (adapters/mod.rs:22) */

@@ -21,5 +21,5 @@ CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
 $CMD > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv --log-file gpurun_out/launches_${R}.csv $CMD > gpurun_out/ncu_launch.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:fft_cta -s 3 -c 2 -o gpurun_out/prof_fft_${R} -f $CMD > gpurun_out/ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:fft1024_warp -s 3 -c 2 -o gpurun_out/prof_fft_${R} -f $CMD > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out | tail -20

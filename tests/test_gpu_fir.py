@@ -57,15 +57,21 @@ def test_fir_strict_c64_and_real_samples(sdr, fmt):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+NO_TENSOR, NO_TCGEN05 = 2, 4  # SDR_FIR_NO_TENSOR, SDR_FIR_NO_TCGEN05
+
+
 @pytest.mark.parametrize("K,tc", [(64, False), (64, True), (255, False)])
-def test_fir_fast_path_within_tolerance_of_f64_truth(sdr, K, tc):
+@pytest.mark.parametrize("flags,path", [(0, 4), (NO_TCGEN05, 3)])
+def test_fir_fast_path_within_tolerance_of_f64_truth(sdr, K, tc, flags, path):
     taps = gen.complex_bandpass_taps(K, 200e3, 100e3, 2.048e6) if tc else gen.lowpass_taps(K, 200e3, 2.048e6)
     iq = gen.tone_noise_u8(1 << 18, 2.048e6, 300e3, 0.5, 0.1, gen.BASE_SEED + 1)
     x = O.unpack_u8iq(iq)
     truth = O.fir_f64(taps, x)
-    f = sdr.Fir(taps, "u8iq")
+    f = sdr.Fir(taps, "u8iq", flags=flags)
     got = f.process(iq)
-    assert f.last_path == 3  # tensor-core Toeplitz path
+    assert f.last_path == path  # 4: tcgen05 integer Toeplitz path, 3: mma.sync Toeplitz path
+    if path == 4:
+        assert rel_err(got, truth) < 1e-6  # exact integer accumulation: only tap quantisation (2^-23 of the largest tap) and the final f32 rounding are left
     e_gpu, e_ref = rel_err(got, truth), rel_err(O.Fir(taps).apply(x), truth)
     assert len(got) == len(x)
     cc = sdr.Fir(taps, "u8iq", flags=2)  # SDR_FIR_NO_TENSOR: CUDA-core FMA path
@@ -84,15 +90,17 @@ def test_fir_impulse_response_is_the_taps(sdr):
         assert np.array_equal(y[:64].real, taps) and np.all(y[64:] == 0) and np.all(y.imag == 0)
 
 
-@pytest.mark.parametrize("strict", [False, True])
-def test_fir_streaming_blocks_equal_one_call(sdr, strict):
+@pytest.mark.parametrize("strict,flags", [(False, 0), (False, NO_TCGEN05), (True, 0)])
+def test_fir_streaming_blocks_equal_one_call(sdr, strict, flags):
     taps = gen.lowpass_taps(255, 100e3, 2.4e6)
     iq = gen.fm_u8(50000, 2.4e6, 75e3, 1e3, 0.05, 21)
-    whole = sdr.Fir(taps, "u8iq", strict=strict).process(iq)
-    f = sdr.Fir(taps, "u8iq", strict=strict)
+    whole = sdr.Fir(taps, "u8iq", strict=strict, flags=flags).process(iq)
+    f = sdr.Fir(taps, "u8iq", strict=strict, flags=flags)
     cuts = [0, 1, 2, 9, 100, 254, 255, 256, 4096, 4097, 20000, 50000]
     parts = np.concatenate([f.process(iq[2 * a:2 * b]) for a, b in zip(cuts[:-1], cuts[1:])])
-    if strict:
+    if strict or flags == 0:
+        # strict order, and the tcgen05 path (exact integer sums): any blocking gives the same bits
+        assert f.last_path == (2 if strict else 4)
         assert np.array_equal(parts.view(np.uint32), whole.view(np.uint32))
     else:
         # tensor path: the grouping of terms into 16-wide MMA steps depends on the block alignment, so different
@@ -134,22 +142,53 @@ def test_tensor_path_shapes(sdr, K, D, tc):
     iq = gen.random_u8(2 * n, 1000 + K + D)
     x = O.unpack_u8iq(iq)
     truth = O.fir_f64(taps, x)[D - 1::D]
-    f = sdr.Fir(taps, "u8iq", decimation=D)
-    a = f.process(iq[:2 * 777])
-    b = f.process(iq[2 * 777:])
-    got = np.concatenate([a, b])
-    assert f.last_path == 3
-    assert len(got) == n // D and rel_err(got, truth) < TOL
+    for flags in ((0, NO_TCGEN05) if D == 1 else (0,)):
+        f = sdr.Fir(taps, "u8iq", decimation=D, flags=flags)
+        a = f.process(iq[:2 * 777])
+        b = f.process(iq[2 * 777:])
+        got = np.concatenate([a, b])
+        assert f.last_path == (4 if (D == 1 and K <= 511 and flags == 0) else 3)
+        assert len(got) == n // D and rel_err(got, truth) < TOL
+
+
+@pytest.mark.parametrize("P", [8, 16, 32])
+@pytest.mark.parametrize("K,tc", [(1, False), (17, True), (64, False), (64, True), (255, False), (255, True), (300, False)])
+def test_tcgen05_path_every_row_width(sdr, monkeypatch, P, K, tc):
+    """The three window-row widths of the tcgen05 kernel (no swizzle / 32-byte / 64-byte swizzled stages) give the
+    same bits: the sums are exact integers, so only the (identical) epilogue rounds."""
+    rng = np.random.default_rng(K * 7 + P)
+    taps = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+    if tc:
+        taps = (taps + 1j * rng.standard_normal(K) / np.sqrt(K)).astype(np.complex64)
+    n = 3 * 4096 + 5
+    iq = gen.random_u8(2 * n, 77 + K)
+    truth = O.fir_f64(taps, O.unpack_u8iq(iq))
+    monkeypatch.setenv("SDR_UMMA_P", str(P))
+    f = sdr.Fir(taps, "u8iq")
+    got = f.process(iq)
+    monkeypatch.setenv("SDR_UMMA_P", "8")
+    ref = sdr.Fir(taps, "u8iq").process(iq)
+    if f.last_path != 4:
+        assert P == 32 and K > 255  # tables of the widest rows do not fit: falls back
+        return
+    assert rel_err(got, truth) < 1e-6
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    # ragged blocks through the carried history: still the same bits
+    f.reset()
+    cuts = [0, 5, 4096, 4101, 8191, 8192 + 3, n]
+    parts = np.concatenate([f.process(iq[2 * a:2 * b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert np.array_equal(parts.view(np.uint32), got.view(np.uint32))
 
 
 def test_tensor_path_multichannel_and_impulse(sdr):
     taps = gen.lowpass_taps(64, 200e3, 2.048e6)
     raw = gen.random_u8(2 * 5 * 4096, 9).reshape(5, -1)
-    f = sdr.Fir(taps, "u8iq", n_channels=5)
-    got = f.process(raw)
-    assert f.last_path == 3
-    for c in range(5):
-        assert rel_err(got[c], O.fir_f64(taps, O.unpack_u8iq(raw[c]))) < TOL
+    for flags, path in ((0, 4), (NO_TCGEN05, 3)):
+        f = sdr.Fir(taps, "u8iq", n_channels=5, flags=flags)
+        got = f.process(raw)
+        assert f.last_path == path
+        for c in range(5):
+            assert rel_err(got[c], O.fir_f64(taps, O.unpack_u8iq(raw[c]))) < TOL
     # impulse: byte 255 at sample 0 over a 128-background is 127/128 * taps, up to f32 rounding of the split sum
     iq = np.full(2 * 300, 128, np.uint8)
     iq[0] = 255

@@ -190,6 +190,9 @@ struct sdr_fir {
     float *d_taps = nullptr;
     uint2 *d_tc_tables = nullptr;  // tensor-core Toeplitz tap fragments (u8 input, non-strict)
     float tc_scale = 1.0f;
+    uint8_t *d_um_tables = nullptr;  // tcgen05 Toeplitz digit tables (u8 input, non-strict, D == 1)
+    int um_P = 0, um_magic[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    float um_sc[3] = {0.0f, 0.0f, 0.0f};
     void *d_hist[2] = {nullptr, nullptr};
     int cur = 0;
     size_t phase = 0;  // inputs already discarded in the current decimation group
@@ -203,6 +206,7 @@ static void fir_free(sdr_fir *f) {
     DeviceGuard g(f->dev);
     if (f->d_taps) cudaFree(f->d_taps);
     if (f->d_tc_tables) cudaFree(f->d_tc_tables);
+    if (f->d_um_tables) cudaFree(f->d_um_tables);
     for (int i = 0; i < 2; ++i)
         if (f->d_hist[i]) cudaFree(f->d_hist[i]);
     f->d_in.release();
@@ -230,6 +234,17 @@ static int fir_alloc(sdr_fir *f, void *user_stream) {
         SDR_CUDA_TRY(cudaMalloc(&f->d_tc_tables, tab.size() * sizeof(uint2)));
         SDR_CUDA_TRY(cudaMemcpyAsync(f->d_tc_tables, tab.data(), tab.size() * sizeof(uint2), cudaMemcpyHostToDevice, f->stream.s));
         SDR_CUDA_TRY(cudaStreamSynchronize(f->stream.s));
+    }
+    if (f->fmt == SDR_FMT_U8IQ && !(f->flags & (SDR_FIR_STRICT_ORDER | SDR_FIR_NO_TENSOR | SDR_FIR_NO_TCGEN05)) && f->D == 1 &&
+        f->K <= 511) {
+        std::vector<uint8_t> tab;
+        const int P = fir_umma_pick_p((int)f->K);
+        if (fir_umma_build_tables(f->taps.data(), (int)f->K, f->taps_complex != 0, P, tab, f->um_magic, f->um_sc)) {
+            f->um_P = P;
+            SDR_CUDA_TRY(cudaMalloc(&f->d_um_tables, tab.size()));
+            SDR_CUDA_TRY(cudaMemcpyAsync(f->d_um_tables, tab.data(), tab.size(), cudaMemcpyHostToDevice, f->stream.s));
+            SDR_CUDA_TRY(cudaStreamSynchronize(f->stream.s));
+        }
     }
     SDR_CUDA_TRY(cudaStreamSynchronize(f->stream.s));
     return SDR_OK;
@@ -321,7 +336,11 @@ static int fir_run_dev(sdr_fir *f, const void *in, size_t n_in, size_t in_stride
     a.K = (int)f->K; a.Kp = (int)f->Kp; a.HL = (int)f->HL; a.D = (int)f->D; a.n_ch = (int)f->n_ch;
     const bool strict = (f->flags & SDR_FIR_STRICT_ORDER) != 0;
     int rc = SDR_ERR_UNSUPPORTED;
-    if (f->d_tc_tables) {
+    if (f->d_um_tables) {
+        rc = fir_umma_launch(a, f->um_P, f->d_um_tables, f->um_magic, f->um_sc, f->stream.s);
+        if (rc == SDR_OK) f->last_path = 4;
+    }
+    if (rc == SDR_ERR_UNSUPPORTED && f->d_tc_tables) {
         rc = fir_tc_launch(a, f->taps_complex != 0, f->d_tc_tables, f->tc_scale, f->stream.s);
         if (rc == SDR_OK) f->last_path = 3;
     }

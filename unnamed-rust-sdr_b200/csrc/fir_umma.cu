@@ -1,0 +1,442 @@
+// fir_umma.cu -- K5: fused u8-IQ FIR on the 5th-generation tensor cores (tcgen05 / TMEM), D == 1.
+//
+// Same reference functions as fir.cu: RtlTcpSignal::next -> signal::Filter::next -> Fir::apply
+// (src/rtltcp.rs:158-164, src/signal/adapters/mod.rs:94-96, src/filter/fir.rs:23-32, src/filter/convolve.rs:13-15).
+//
+// The raw rtl_tcp bytes are NEVER converted: they are the A operand of an integer Toeplitz GEMM.
+//
+//   y[m] = 2^-(S+7) * sum_k  t[k] * (b[m-k] - 128)          t[k] = round(c[k] * 2^S)  (|t| < 2^23)
+//        = 2^-(S+7) * ( sum_k t[k] b[m-k]  -  128 sum_k t[k] )
+//
+//   * A (M = 128 rows, K-major, u8): row i of a tile is the window of interleaved I,Q BYTES that starts 2P bytes after
+//     row i-1.  A shared-memory matrix descriptor whose rows overlap (row pitch 2P bytes inside ONE flat copy of the
+//     input: pitch 16 B = no swizzle, 32 B = SWIZZLE_32B, 64 B = SWIZZLE_64B) reads exactly that Hankel matrix, so the
+//     input is staged once, untouched, by cp.async straight from global memory (scripts/probes/umma_toeplitz_probe.cu
+//     is the hardware check: the swizzle XOR is a function of the absolute shared address, so overlapping rows agree).
+//   * B (N = 6P columns, K-major, s8): banded Toeplitz block of the integer taps, split into three balanced base-256
+//     digits; column (digit d, phase j, part q) holds digit d of the taps that produce the I (q=0) or Q (q=1) part of
+//     output P*i + j.  Real taps touch only the I (or Q) bytes of the window; complex taps touch both
+//     (y.re = x.re c.re - x.im c.im, y.im = x.re c.im + x.im c.re: the signs live in the table).
+//   * D (TMEM, s32): exact integer sums.  |sum| <= 255*128*K < 2^31 and |sum - 128 sum_k d| <= 2^14 K < 2^23 for
+//     K <= 511, so the epilogue converts with the 1.5*2^23 magic-number add (no I2F) and combines the three digits with
+//     two FFMAs: the result is the exactly-accumulated dot product rounded ~once -- closer to the f64 truth than the
+//     reference's own sequential f32 sum (tests/test_gpu_fir.py bars: 1e-5 relative, and <= 4x the reference's error).
+//
+// Warp roles (one persistent CTA per SM, 320 threads):
+//   warp 0      producer: cp.async 16-byte chunks global -> (swizzled) stage, completion on an mbarrier
+//                          (cp.async.mbarrier.arrive.noinc); history / zero padding at the stream start by plain stores
+//   warp 1      MMA issuer: one lane issues KS * MB tcgen05.mma.kind::i8 per tile, tcgen05.commit frees the stage and
+//                          publishes the accumulator set
+//   warps 2..9  two epilogue warpgroups (one per accumulator set): tcgen05.ld -> digits -> f32 -> XOR-swizzled
+//               warp-private staging -> 512-byte coalesced global stores
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "kernels.h"
+
+namespace sdr {
+
+namespace {
+
+constexpr int UM_STAGES = 4;
+constexpr int UM_STAGE_BYTES = 10240;  // 8 KB of window starts per tile + (KS*32 B) halo; multiple of 1024 (swizzle period)
+constexpr int UM_TILE_OUT = 4096;      // outputs per tile = 128 * MB * P
+constexpr int UM_ACC_COLS = 192;       // TMEM columns per accumulator set = MB * 6P
+constexpr int UM_THREADS = 320;
+constexpr int UM_MAX_K = 511;
+
+struct UmArgs {
+    FirArgs f;
+    const uint8_t *tab;  // this call's alignment variant: KS blocks of N*32 bytes in canonical no-swizzle K-major order
+    int KS;              // k-steps of 32 bytes = 16 samples
+    int delta;           // window start is `delta` samples left of the first needed sample (16-byte alignment)
+    int ntiles;          // tiles per channel
+    int magic[2][3];     // [part][digit]: 0x4B400000 - 128 * sum of that column's digits
+    float sc[3];         // 2^-(S+7) * {1, 256, 65536}
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async16_s(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
+                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor (K-major): start address, leading / stride byte offsets (16-byte units), version 1
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFFu) << 32) | ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+
+template <int P> struct UmLayout;
+template <> struct UmLayout<8>  { static constexpr uint32_t type = 0; __device__ static uint32_t swz(uint32_t o) { return o; } };
+template <> struct UmLayout<16> { static constexpr uint32_t type = 6; __device__ static uint32_t swz(uint32_t o) { return o ^ (((o >> 7) & 1u) << 4); } };
+template <> struct UmLayout<32> { static constexpr uint32_t type = 4; __device__ static uint32_t swz(uint32_t o) { return o ^ (((o >> 7) & 3u) << 4); } };
+
+__host__ __device__ constexpr size_t um_smem_bytes(int P, int KS) {
+    // tables + stages + epilogue staging (8 warps x 32 rows x P*8 B) + 1 KB alignment slack + barriers
+    return (size_t)KS * 6 * P * 32 + (size_t)UM_STAGES * UM_STAGE_BYTES + (size_t)8 * 32 * P * 8 + 1024 + 256;
+}
+
+template <int P>
+__global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a) {
+    constexpr int MB = 32 / P;               // 128-row blocks per tile
+    constexpr int N = 6 * P;                 // MMA N: 3 digits x P phases x (I, Q)
+    constexpr int ROWB = 2 * P;              // bytes between window rows
+    constexpr int CPR = P / 2;               // 16-byte chunks per staged output row (P complex f32)
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * UM_STAGES + 4];
+    __shared__ uint32_t tmem_base_s;
+    const FirArgs &f = a.f;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KS = a.KS;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // stages first: 1024-aligned for the swizzle modes
+    const uint32_t stage0 = base;
+    const uint32_t tab_s = stage0 + UM_STAGES * UM_STAGE_BYTES;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));        // generic pointer to `base`
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (UM_STAGES + s); };
+    auto accf_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + s); };
+    auto acce_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + 2 + s); };
+
+    // ---- one-time setup ----
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.tab);
+        uint4 *dst = reinterpret_cast<uint4 *>(gen + UM_STAGES * UM_STAGE_BYTES);
+        for (int i = tid; i < KS * N * 2; i += UM_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full_bar(s), 32); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();  // the tap tables were written through the generic proxy, tcgen05.mma reads through the async one
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    const long long nwork = (long long)a.ntiles * f.n_ch;
+    const long long wstride = gridDim.x;
+
+    if (warp == 0) {
+        // ================= producer =================
+        const int nchunks = (ROWB * (128 * MB - 1) + 32 * KS + 15) / 16;
+        int stage = 0;
+        uint32_t ph = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride) {
+            const int ch = (int)(w / a.ntiles);
+            const long long m0 = (w % a.ntiles) * UM_TILE_OUT;
+            const long long w0 = f.first + m0 - (f.K - 1) - a.delta;  // multiple of 8 samples
+            const unsigned char *in = (const unsigned char *)f.in + (long long)ch * f.in_stride * 2;
+            const unsigned char *hist = (const unsigned char *)f.hist + (long long)ch * f.hist_stride * 2;
+            mbar_wait(empty_bar(stage), ph ^ 1u);
+            const uint32_t sbase = stage0 + (uint32_t)stage * UM_STAGE_BYTES;
+            bool slow = false;
+            for (int c = lane; c < nchunks; c += 32) {
+                const long long s0 = w0 + 8LL * c;
+                const uint32_t off = UmLayout<P>::swz(16u * (uint32_t)c);
+                if (s0 >= 0 && s0 + 8 <= f.n_in) {
+                    cp_async16_s(sbase + off, in + 2 * s0);
+                } else if (s0 < f.n_in) {
+                    // stream start (carried history, then "zero" samples = byte pair 128,128) or the ragged end
+                    unsigned short h[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const long long s = s0 + i;
+                        unsigned short v = 0x8080;
+                        if (s >= 0) { if (s < f.n_in) v = *reinterpret_cast<const unsigned short *>(in + 2 * s); }
+                        else if (s >= -(long long)f.HL) v = *reinterpret_cast<const unsigned short *>(hist + 2 * ((long long)f.HL + s));
+                        h[i] = v;
+                    }
+                    uint4 q;
+                    q.x = h[0] | ((unsigned)h[1] << 16); q.y = h[2] | ((unsigned)h[3] << 16);
+                    q.z = h[4] | ((unsigned)h[5] << 16); q.w = h[6] | ((unsigned)h[7] << 16);
+                    *reinterpret_cast<uint4 *>(gen + (size_t)stage * UM_STAGE_BYTES + off) = q;
+                    slow = true;
+                }
+                // chunks entirely past the end feed only rows whose outputs are never stored: left as they are
+            }
+            if (slow) fence_proxy_async();
+            cp_async_arrive_noinc(full_bar(stage));
+            if (++stage == UM_STAGES) { stage = 0; ph ^= 1u; }
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (warp == 1) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t bdesc0 = smem_desc(tab_s, 128, 256, 0);
+        int stage = 0, as = 0;
+        uint32_t ph = 0, aph = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride) {
+            mbar_wait(full_bar(stage), ph);
+            mbar_wait(acce_bar(as), aph ^ 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint64_t adesc0 = smem_desc(stage0 + (uint32_t)stage * UM_STAGE_BYTES, 16, 8 * ROWB, UmLayout<P>::type);
+                const uint32_t d0 = tmem + (uint32_t)(as * UM_ACC_COLS);
+                for (int kk = 0; kk < KS; ++kk) {
+                    const uint64_t bd = bdesc0 + (uint64_t)((kk * N * 32) >> 4);
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb)
+                        umma_i8(d0 + mb * N, adesc0 + (uint64_t)((mb * 128 * ROWB + kk * 32) >> 4), bd, idesc, kk > 0);
+                }
+                umma_commit(empty_bar(stage));  // the stage may be refilled once these MMAs have read it
+                umma_commit(accf_bar(as));      // ... and the accumulator set is complete
+            }
+            __syncwarp();
+            if (++stage == UM_STAGES) { stage = 0; ph ^= 1u; }
+            as ^= 1;
+            if (as == 0) aph ^= 1u;
+        }
+    } else {
+        // ================= epilogue: warpgroup g owns accumulator set g =================
+        const int ew = warp - 2, g = ew >> 2;
+        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        uint8_t *stg = gen + (size_t)UM_STAGES * UM_STAGE_BYTES + (size_t)KS * N * 32 + (size_t)ew * 32 * P * 8;
+        const float sc0 = a.sc[0], sc1 = a.sc[1], sc2 = a.sc[2];
+        const int mg[2][3] = {{a.magic[0][0], a.magic[0][1], a.magic[0][2]}, {a.magic[1][0], a.magic[1][1], a.magic[1][2]}};
+        uint32_t aph = 0;
+        long long it = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
+            if ((it & 1) != g) continue;
+            const int ch = (int)(w / a.ntiles);
+            const long long m0 = (w % a.ntiles) * UM_TILE_OUT;
+            float2 *out = (float2 *)f.out + (long long)ch * f.out_stride;
+            mbar_wait(accf_bar(g), aph);
+            tc_fence_after();
+            const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * UM_ACC_COLS);
+#pragma unroll 1
+            for (int mb = 0; mb < MB; ++mb) {
+#pragma unroll 1
+                for (int pc = 0; pc < P / 8; ++pc) {
+                    uint32_t v0[16], v1[16], v2[16];
+                    const uint32_t col = tbase + (uint32_t)(mb * N + 16 * pc);
+                    tmem_ld16(col, v0);
+                    tmem_ld16(col + 2 * P, v1);
+                    tmem_ld16(col + 4 * P, v2);
+                    tmem_ld_wait();
+                    if (mb == MB - 1 && pc == P / 8 - 1) {
+                        // every accumulator of this set is in registers: hand the set back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(acce_bar(g));
+                    }
+                    float y[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const float f0 = __int_as_float((int)v0[i] + mg[i & 1][0]) - 12582912.0f;
+                        const float f1 = __int_as_float((int)v1[i] + mg[i & 1][1]) - 12582912.0f;
+                        const float f2 = __int_as_float((int)v2[i] + mg[i & 1][2]) - 12582912.0f;
+                        y[i] = fmaf(f2, sc2, fmaf(f1, sc1, f0 * sc0));
+                    }
+                    // row `lane` of the warp's staging tile, chunks 4pc .. 4pc+3, XOR-swizzled: conflict-free both ways
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int c = 4 * pc + q;
+                        const int pcn = (P == 8) ? (c ^ ((lane >> 1) & 3)) : (c ^ (lane & 7));
+                        *reinterpret_cast<float4 *>(stg + ((size_t)lane * CPR + pcn) * 16) =
+                            make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                    }
+                }
+                __syncwarp();
+                // the warp's 32 rows are 32*P consecutive outputs: 512 contiguous bytes per store instruction
+                const long long mrow = m0 + (long long)(mb * 128 + quad * 32) * P;
+#pragma unroll
+                for (int i = 0; i < CPR; ++i) {
+                    const int q = i * 32 + lane;
+                    const int row = q / CPR, c = q % CPR;
+                    const int pcn = (P == 8) ? (c ^ ((row >> 1) & 3)) : (c ^ (row & 7));
+                    const float4 val = *reinterpret_cast<const float4 *>(stg + ((size_t)row * CPR + pcn) * 16);
+                    const long long m = mrow + 2LL * q;
+                    if (m + 1 < f.n_out) *reinterpret_cast<float4 *>(out + m) = val;
+                    else if (m < f.n_out) out[m] = make_float2(val.x, val.y);
+                }
+                __syncwarp();
+            }
+            aph ^= 1u;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
+// balanced base-256 digits of t: t = d0 + 256 d1 + 65536 d2, d0, d1 in [-128, 127]; false if d2 leaves that range
+inline bool digits3(long long t, int d[3]) {
+    for (int i = 0; i < 2; ++i) {
+        long long r = ((t % 256) + 256) % 256;
+        if (r >= 128) r -= 256;
+        d[i] = (int)r;
+        t = (t - r) / 256;
+    }
+    d[2] = (int)t;
+    return t >= -128 && t <= 127;
+}
+
+}  // namespace
+
+int fir_umma_ksteps(int K, int P) { return (K + P + 6 + 15) / 16; }
+
+int fir_umma_pick_p(int K) {
+    if (const char *e = std::getenv("SDR_UMMA_P")) {
+        const int p = std::atoi(e);
+        if (p == 8 || p == 16 || p == 32) return p;
+    }
+    // cycles per output ~ KS(P) * max(45, (4096 + 192 P) / 128) / (128 P): wide rows amortise the window reads
+    int best = 8;
+    double best_c = 1e30;
+    for (int p : {8, 16, 32}) {
+        const int ks = fir_umma_ksteps(K, p);
+        if (um_smem_bytes(p, ks) > 220 * 1024 || 32 * ks + 8192 - 2 * p > UM_STAGE_BYTES) continue;
+        const double c = ks * std::max(45.0, (4096.0 + 192.0 * p) / 128.0) / (128.0 * p);
+        if (c < best_c) { best_c = c; best = p; }
+    }
+    return best;
+}
+
+// host: the 8 alignment variants of the Toeplitz tap table.  Layout [delta][kk][canonical N x 32 B block]:
+// element (n, kb) of a block sits at (n/8)*256 + (kb/16)*128 + (n%8)*16 + kb%16 (no-swizzle K-major core matrices).
+bool fir_umma_build_tables(const float *taps, int K, bool tc, int P, std::vector<uint8_t> &out, int magic[2][3], float sc[3]) {
+    if (K < 1 || K > UM_MAX_K) return false;
+    const int KS = fir_umma_ksteps(K, P), N = 6 * P, W = tc ? 2 : 1;
+    float cmax = 0.0f;
+    for (int i = 0; i < K * W; ++i) {
+        if (!std::isfinite(taps[i])) return false;
+        cmax = std::fmax(cmax, std::fabs(taps[i]));
+    }
+    int e = 0;
+    if (cmax > 0.0f) std::frexp(cmax, &e);
+    int S = 23 - e;  // cmax * 2^S in [2^22, 2^23)
+    std::vector<long long> t((size_t)K * W);
+    for (;; --S) {
+        bool ok = true;
+        for (int i = 0; i < K * W && ok; ++i) {
+            t[i] = std::llround(std::ldexp((double)taps[i], S));
+            int d[3];
+            ok = digits3(t[i], d) && digits3(-t[i], d);
+        }
+        if (ok) break;
+    }
+    // digit tables of the four roles a tap can play: +re, -im (into the I part), +im, +re (into the Q part)
+    auto digit = [&](int k, int part, int q, int dg) -> int {
+        long long v;
+        if (!tc) v = (q == part) ? t[k] : 0;
+        else if (part == 0) v = (q == 0) ? t[2 * k] : -t[2 * k + 1];
+        else v = (q == 0) ? t[2 * k + 1] : t[2 * k];
+        int d[3];
+        digits3(v, d);
+        return d[dg];
+    };
+    for (int part = 0; part < 2; ++part)
+        for (int dg = 0; dg < 3; ++dg) {
+            long long s = 0;
+            for (int k = 0; k < K; ++k) s += digit(k, part, 0, dg) + digit(k, part, 1, dg);
+            magic[part][dg] = (int)(0x4B400000LL - 128 * s);
+        }
+    const float base = std::ldexp(1.0f, -S - 7);
+    sc[0] = base; sc[1] = base * 256.0f; sc[2] = base * 65536.0f;
+    out.assign((size_t)8 * KS * N * 32, 0);
+    for (int delta = 0; delta < 8; ++delta)
+        for (int kk = 0; kk < KS; ++kk) {
+            uint8_t *blk = out.data() + ((size_t)delta * KS + kk) * N * 32;
+            for (int n = 0; n < N; ++n) {
+                const int dg = n / (2 * P), j = (n % (2 * P)) / 2, part = n & 1;
+                for (int kb = 0; kb < 32; ++kb) {
+                    const int s = kk * 16 + kb / 2, q = kb & 1;
+                    const int k = K - 1 + delta + j - s;
+                    int v = 0;
+                    if (k >= 0 && k < K) v = digit(k, part, q, dg);
+                    blk[(n / 8) * 256 + (kb / 16) * 128 + (n % 8) * 16 + kb % 16] = (uint8_t)(int8_t)v;
+                }
+            }
+        }
+    return true;
+}
+
+// returns SDR_ERR_UNSUPPORTED when this path does not apply (caller falls back to the mma.sync / CUDA-core kernels)
+int fir_umma_launch(const FirArgs &f, int P, const uint8_t *d_tables, const int magic[2][3], const float sc[3], cudaStream_t st) {
+    if (f.n_out <= 0) return SDR_OK;
+    if (f.D != 1 || f.K > UM_MAX_K) return SDR_ERR_UNSUPPORTED;
+    if (((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 15) || (f.out_stride & 1) || (f.in_stride & 7) || ((uintptr_t)f.hist & 1))
+        return SDR_ERR_UNSUPPORTED;
+    const int KS = fir_umma_ksteps(f.K, P);
+    const size_t smem = um_smem_bytes(P, KS);
+    if (smem > 220 * 1024 || 32 * KS + 8192 - 2 * P > UM_STAGE_BYTES) return SDR_ERR_UNSUPPORTED;
+    UmArgs a;
+    a.f = f;
+    a.KS = KS;
+    long long d = (f.first - (f.K - 1)) % 8;
+    if (d < 0) d += 8;
+    a.delta = (int)d;
+    a.tab = d_tables + (size_t)d * KS * 6 * P * 32;
+    a.ntiles = (int)((f.n_out + UM_TILE_OUT - 1) / UM_TILE_OUT);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 3; ++j) a.magic[i][j] = magic[i][j];
+    for (int j = 0; j < 3; ++j) a.sc[j] = sc[j];
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long nwork = (long long)a.ntiles * f.n_ch;
+    const unsigned grid = (unsigned)std::min<long long>(nwork, sms);
+    auto go = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e);
+        kern<<<grid, UM_THREADS, smem, st>>>(a);
+        count_launch();
+        return launch_status();
+    };
+    switch (P) {
+        case 8: return go(fir_umma_kernel<8>);
+        case 16: return go(fir_umma_kernel<16>);
+        case 32: return go(fir_umma_kernel<32>);
+    }
+    return SDR_ERR_UNSUPPORTED;
+}
+
+}  // namespace sdr
