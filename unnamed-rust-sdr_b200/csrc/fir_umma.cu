@@ -172,29 +172,37 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
             mbar_wait(empty_bar(stage), ph ^ 1u);
             const uint32_t sbase = stage0 + (uint32_t)stage * UM_STAGE_BYTES;
             bool slow = false;
-            for (int c = lane; c < nchunks; c += 32) {
-                const long long s0 = w0 + 8LL * c;
-                const uint32_t off = UmLayout<P>::swz(16u * (uint32_t)c);
-                if (s0 >= 0 && s0 + 8 <= f.n_in) {
-                    cp_async16_s(sbase + off, in + 2 * s0);
-                } else if (s0 < f.n_in) {
-                    // stream start (carried history, then "zero" samples = byte pair 128,128) or the ragged end
-                    unsigned short h[8];
+            if (w0 >= 0 && w0 + 8LL * nchunks <= f.n_in) {
+                // interior tile (all but the first / last of a block): nothing but address arithmetic and LDGSTS
+                const unsigned char *src = in + 2 * w0;
+#pragma unroll 4
+                for (int c = lane; c < nchunks; c += 32)
+                    cp_async16_s(sbase + UmLayout<P>::swz(16u * (uint32_t)c), src + 16 * c);
+            } else {
+                for (int c = lane; c < nchunks; c += 32) {
+                    const long long s0 = w0 + 8LL * c;
+                    const uint32_t off = UmLayout<P>::swz(16u * (uint32_t)c);
+                    if (s0 >= 0 && s0 + 8 <= f.n_in) {
+                        cp_async16_s(sbase + off, in + 2 * s0);
+                    } else if (s0 < f.n_in) {
+                        // stream start (carried history, then "zero" samples = byte pair 128,128) or the ragged end
+                        unsigned short h[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const long long s = s0 + i;
-                        unsigned short v = 0x8080;
-                        if (s >= 0) { if (s < f.n_in) v = *reinterpret_cast<const unsigned short *>(in + 2 * s); }
-                        else if (s >= -(long long)f.HL) v = *reinterpret_cast<const unsigned short *>(hist + 2 * ((long long)f.HL + s));
-                        h[i] = v;
+                        for (int i = 0; i < 8; ++i) {
+                            const long long s = s0 + i;
+                            unsigned short v = 0x8080;
+                            if (s >= 0) { if (s < f.n_in) v = *reinterpret_cast<const unsigned short *>(in + 2 * s); }
+                            else if (s >= -(long long)f.HL) v = *reinterpret_cast<const unsigned short *>(hist + 2 * ((long long)f.HL + s));
+                            h[i] = v;
+                        }
+                        uint4 q;
+                        q.x = h[0] | ((unsigned)h[1] << 16); q.y = h[2] | ((unsigned)h[3] << 16);
+                        q.z = h[4] | ((unsigned)h[5] << 16); q.w = h[6] | ((unsigned)h[7] << 16);
+                        *reinterpret_cast<uint4 *>(gen + (size_t)stage * UM_STAGE_BYTES + off) = q;
+                        slow = true;
                     }
-                    uint4 q;
-                    q.x = h[0] | ((unsigned)h[1] << 16); q.y = h[2] | ((unsigned)h[3] << 16);
-                    q.z = h[4] | ((unsigned)h[5] << 16); q.w = h[6] | ((unsigned)h[7] << 16);
-                    *reinterpret_cast<uint4 *>(gen + (size_t)stage * UM_STAGE_BYTES + off) = q;
-                    slow = true;
+                    // chunks entirely past the end feed only rows whose outputs are never stored: left as they are
                 }
-                // chunks entirely past the end feed only rows whose outputs are never stored: left as they are
             }
             if (slow) fence_proxy_async();
             cp_async_arrive_noinc(full_bar(stage));
@@ -245,53 +253,70 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
             mbar_wait(accf_bar(g), aph);
             tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * UM_ACC_COLS);
-#pragma unroll 1
-            for (int mb = 0; mb < MB; ++mb) {
-#pragma unroll 1
-                for (int pc = 0; pc < P / 8; ++pc) {
-                    uint32_t v0[16], v1[16], v2[16];
-                    const uint32_t col = tbase + (uint32_t)(mb * N + 16 * pc);
-                    tmem_ld16(col, v0);
-                    tmem_ld16(col + 2 * P, v1);
-                    tmem_ld16(col + 4 * P, v2);
-                    tmem_ld_wait();
-                    if (mb == MB - 1 && pc == P / 8 - 1) {
-                        // every accumulator of this set is in registers: hand the set back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(acce_bar(g));
-                    }
-                    float y[16];
+            // 4 pieces per tile (MB * P/8 == 4): piece = 8 phases of one 128-row block = 16 columns of each digit.
+            // The TMEM loads of piece i+1 are in flight while piece i is converted and staged.
+            constexpr int PPB = P / 8;  // pieces per 128-row block
+            uint32_t v[2][3][16];
+            auto issue = [&](int pi, uint32_t (&d)[3][16]) {
+                const uint32_t col = tbase + (uint32_t)((pi / PPB) * N + 16 * (pi % PPB));
+                tmem_ld16(col, d[0]);
+                tmem_ld16(col + 2 * P, d[1]);
+                tmem_ld16(col + 4 * P, d[2]);
+            };
+            issue(0, v[0]);
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float f0 = __int_as_float((int)v0[i] + mg[i & 1][0]) - 12582912.0f;
-                        const float f1 = __int_as_float((int)v1[i] + mg[i & 1][1]) - 12582912.0f;
-                        const float f2 = __int_as_float((int)v2[i] + mg[i & 1][2]) - 12582912.0f;
-                        y[i] = fmaf(f2, sc2, fmaf(f1, sc1, f0 * sc0));
-                    }
-                    // row `lane` of the warp's staging tile, chunks 4pc .. 4pc+3, XOR-swizzled: conflict-free both ways
+            for (int pi = 0; pi < 4; ++pi) {
+                const int mb = pi / PPB, pc = pi % PPB;
+                tmem_ld_wait();
+                if (pi + 1 < 4) issue(pi + 1, v[(pi + 1) & 1]);
+                uint32_t (&d)[3][16] = v[pi & 1];
+                float y[16];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int c = 4 * pc + q;
-                        const int pcn = (P == 8) ? (c ^ ((lane >> 1) & 3)) : (c ^ (lane & 7));
-                        *reinterpret_cast<float4 *>(stg + ((size_t)lane * CPR + pcn) * 16) =
-                            make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-                    }
+                for (int i = 0; i < 16; ++i) {
+                    const float f0 = __int_as_float((int)d[0][i] + mg[i & 1][0]) - 12582912.0f;
+                    const float f1 = __int_as_float((int)d[1][i] + mg[i & 1][1]) - 12582912.0f;
+                    const float f2 = __int_as_float((int)d[2][i] + mg[i & 1][2]) - 12582912.0f;
+                    y[i] = fmaf(f2, sc2, fmaf(f1, sc1, f0 * sc0));
                 }
-                __syncwarp();
-                // the warp's 32 rows are 32*P consecutive outputs: 512 contiguous bytes per store instruction
-                const long long mrow = m0 + (long long)(mb * 128 + quad * 32) * P;
-#pragma unroll
-                for (int i = 0; i < CPR; ++i) {
-                    const int q = i * 32 + lane;
-                    const int row = q / CPR, c = q % CPR;
-                    const int pcn = (P == 8) ? (c ^ ((row >> 1) & 3)) : (c ^ (row & 7));
-                    const float4 val = *reinterpret_cast<const float4 *>(stg + ((size_t)row * CPR + pcn) * 16);
-                    const long long m = mrow + 2LL * q;
-                    if (m + 1 < f.n_out) *reinterpret_cast<float4 *>(out + m) = val;
-                    else if (m < f.n_out) out[m] = make_float2(val.x, val.y);
+                if (pi == 3) {
+                    // every accumulator of this set is in registers: hand the set back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acce_bar(g));
                 }
-                __syncwarp();
+                // row `lane` of the warp's staging tile, chunks 4pc .. 4pc+3, XOR-swizzled: conflict-free both ways
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int c = 4 * pc + q;
+                    const int pcn = (P == 8) ? (c ^ ((lane >> 1) & 3)) : (c ^ (lane & 7));
+                    *reinterpret_cast<float4 *>(stg + ((size_t)lane * CPR + pcn) * 16) =
+                        make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                }
+                if (pc == PPB - 1) {
+                    __syncwarp();
+                    // the warp's 32 rows are 32*P consecutive outputs: 512 contiguous bytes per store instruction
+                    const long long mrow = m0 + (long long)(mb * 128 + quad * 32) * P;
+                    float4 val[CPR];
+#pragma unroll
+                    for (int i = 0; i < CPR; ++i) {
+                        const int q = i * 32 + lane;
+                        const int row = q / CPR, c = q % CPR;
+                        const int pcn = (P == 8) ? (c ^ ((row >> 1) & 3)) : (c ^ (row & 7));
+                        val[i] = *reinterpret_cast<const float4 *>(stg + ((size_t)row * CPR + pcn) * 16);
+                    }
+                    if (mrow + 32 * P <= f.n_out) {
+#pragma unroll
+                        for (int i = 0; i < CPR; ++i) *reinterpret_cast<float4 *>(out + mrow + 2 * (i * 32 + lane)) = val[i];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < CPR; ++i) {
+                            const long long m = mrow + 2LL * (i * 32 + lane);
+                            if (m + 1 < f.n_out) *reinterpret_cast<float4 *>(out + m) = val[i];
+                            else if (m < f.n_out) out[m] = make_float2(val[i].x, val[i].y);
+                        }
+                    }
+                    __syncwarp();
+                }
             }
             aph ^= 1u;
         }
