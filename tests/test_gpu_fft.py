@@ -34,6 +34,19 @@ def test_pow2_sizes_c64(sdr, logn):
     assert np.abs(O.dft_f64(x[0]) - np.fft.fft(x[0].astype(np.complex128))).max() < 1e-9 * n
 
 
+@pytest.mark.parametrize("logn,batches", [(14, 700), (15, 300), (16, 150)])
+def test_large_n_many_transforms_steady_state(sdr, logn, batches):
+    """n >= 2^14 runs the four-step passes in one persistent launch with per-transform dependencies; enough
+    transforms that second-step items trail first-step items of later transforms (the steady state), u8 and c64."""
+    n = 1 << logn
+    x = gen.complex_noise(batches * n, 77 + logn).reshape(batches, n)
+    got = sdr.FftPlan(n, "c64", shift=True, norm=True).exec(x)
+    check(got, x, shift=True, norm=True)
+    raw = gen.random_u8(2 * 20 * n, logn)
+    got = sdr.FftPlan(n, "u8iq").exec(raw)
+    check(got, O.unpack_u8iq(raw).reshape(20, n))
+
+
 @pytest.mark.parametrize("logn", [8, 10, 12, 14, 16])
 def test_shift_norm_are_exact_permutation_and_scale(sdr, logn):
     n = 1 << logn

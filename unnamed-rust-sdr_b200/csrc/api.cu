@@ -447,7 +447,7 @@ struct sdr_fft {
     size_t m = 0;
     int log_m = 0;
     float2 *d_chirp = nullptr, *d_bfft = nullptr;
-    DevBuf d_a1, d_a2;
+    DevBuf d_a1, d_a2, d_work;
     DevBuf d_in, d_out, d_in2, d_out2;
     HostPipe pipe;
 };
@@ -458,7 +458,7 @@ static void fft_free(sdr_fft *p) {
     if (p->d_tw) cudaFree(p->d_tw);
     if (p->d_chirp) cudaFree(p->d_chirp);
     if (p->d_bfft) cudaFree(p->d_bfft);
-    p->d_a1.release(); p->d_a2.release(); p->d_in.release(); p->d_out.release(); p->d_in2.release(); p->d_out2.release();
+    p->d_a1.release(); p->d_a2.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_in2.release(); p->d_out2.release();
     p->pipe.release();
     p->stream.release();
     delete p;
@@ -559,6 +559,11 @@ static int fft_run_dev(sdr_fft *p, const void *in, size_t batches, float *out) {
         FftArgs a;
         a.in = in; a.out = (float2 *)out; a.tw = p->d_tw; a.batches = (long long)batches; a.log_n = p->log_n;
         a.fmt = p->fmt; a.flags = p->flags; a.norm = p->norm;
+        if (p->log_n >= 13) {
+            const int rc = p->d_work.reserve((batches + 1) * sizeof(int));
+            if (rc) return rc;
+            a.work = (int *)p->d_work.p;
+        }
         return fft_pow2_launch(a, st);
     }
     if (p->mode == 1)
@@ -567,6 +572,8 @@ static int fft_run_dev(sdr_fft *p, const void *in, size_t batches, float *out) {
     const size_t slab = std::max<size_t>(1, std::min<size_t>(batches, ((size_t)64 << 20) / (p->m * sizeof(float2))));
     int rc = p->d_a1.reserve(slab * p->m * sizeof(float2));
     if (!rc) rc = p->d_a2.reserve(slab * p->m * sizeof(float2));
+    if (rc) return rc;
+    if (p->log_m >= 14) rc = p->d_work.reserve((slab + 1) * sizeof(int));
     if (rc) return rc;
     const size_t out_len = sdr_fft_output_len(p);
     for (size_t b0 = 0; b0 < batches; b0 += slab) {
@@ -578,6 +585,7 @@ static int fft_run_dev(sdr_fft *p, const void *in, size_t batches, float *out) {
         FftArgs a;
         a.in = a1; a.out = a2; a.tw = p->d_tw; a.batches = (long long)nb; a.log_n = p->log_m; a.fmt = SDR_FMT_C64;
         a.flags = 0; a.norm = 1.0f;
+        if (p->log_m >= 14) a.work = (int *)p->d_work.p;
         rc = fft_pow2_launch(a, st);
         if (rc) return rc;
         rc = bluestein_mul_launch(a2, p->d_bfft, (long long)nb, (int)p->m, st);

@@ -13,6 +13,8 @@
 //   n = 32768, 65536   two kernels (four-step): 256-point column FFTs, then (n/256)-point column
 //                      FFTs with the W_n^{k r} twiddle folded into the load.  The intermediate is
 //                      written in place in the output buffer.
+#include <cstdlib>
+
 #include "kernels.h"
 
 namespace sdr {
@@ -523,6 +525,173 @@ __global__ void __launch_bounds__(16 * ((1 << LOGL) / 16)) fft_cols_kernel(FftAr
     }
 }
 
+// ---- n = 2^14 .. 2^16: four-step in ONE persistent launch, intermediate kept in L2 ------------------------------
+// n = 256 * N2 (N2 = 64, 128, 256).  Work items of 4096 elements, handed out in ticket order:
+//   STEP 0 (transform b, tile j): the 16 columns 16j.. of the [256][N2] view; 256-point FFT down each column; result
+//          row-major scratch[256 c + k2] in the OUTPUT buffer.  global -> registers (radix 16) -> shared -> registers
+//          (radix 16) -> global: one shared exchange, 128-byte segments on both sides.
+//   STEP 1 (transform b, tile j): the NC = 4096/N2 adjacent columns k of the [N2][256] view of the scratch, element
+//          (r, k) times W_n^{k r}; N2-point FFT down each column; bin k1 is X[k + 256 k1].  Reads and writes the
+//          same address set, so it runs in place.
+// Items are ordered wave by wave: STEP 0 of transform g, then STEP 1 of transform g - LAG, with LAG large enough that
+// every resident CTA holds an earlier ticket by the time a STEP 1 item is taken.  A STEP 1 item waits (acquire spin
+// on a per-transform counter that STEP 0 items bump after a release fence) for its transform's columns; tickets are
+// served in order by CTAs that are all resident, so the wait always ends.  The scratch of the ~LAG transforms in
+// flight (about 10 MB) never leaves the 126 MB L2: HBM sees 8 B/sample in and 8 B/sample out, as for small n.
+// W_n^{k r} is generated per thread from two exact table entries (W_n^{k t}, W_n^{k TC}) by a depth-4 product tree.
+template <int LOGN2> struct L2Plan {
+    static constexpr int N2 = 1 << LOGN2, NC = 4096 / N2, TC = N2 / 16, R2 = N2 / 16, NB2 = 16 / R2, S = N2 / 16;
+    static constexpr int SSTRIDE0 = padlen(256), SSTRIDE1 = padlen(N2);
+    static constexpr int SM_ELEMS = (16 * SSTRIDE0 > NC * SSTRIDE1) ? 16 * SSTRIDE0 : NC * SSTRIDE1;
+    static constexpr size_t smem_bytes() { return (size_t)(SM_ELEMS + 15 * 16 + (R2 - 1) * 16) * sizeof(float2); }
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int LOGN2, int FMT>
+__global__ void __launch_bounds__(256, 3) fft_l2_kernel(FftArgs a, int lag, long long total_items) {
+    using PL = L2Plan<LOGN2>;
+    constexpr int N2 = PL::N2, NC = PL::NC, TC = PL::TC, R2 = PL::R2, NB2 = PL::NB2, S = PL::S;
+    constexpr int n = 256 * N2;
+    extern __shared__ float4 smem4[];
+    __shared__ long long s_item;
+    float2 *sm = reinterpret_cast<float2 *>(smem4);
+    float2 *tw0 = sm + PL::SM_ELEMS;   // W_256^{q t}, q = 1..15, t < 16
+    float2 *tw1 = tw0 + 15 * 16;       // W_N2^{s k}, s = 1..R2-1, k < 16
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 15 * 16; i += 256) tw0[i] = __ldg(a.tw + (long long)((i / 16 + 1) * (i % 16)) * (n / 256));
+    for (int i = tid; i < (R2 - 1) * 16; i += 256) tw1[i] = __ldg(a.tw + (long long)((i / 16 + 1) * (i % 16)) * 256);
+    int *ticket = a.work, *flags = a.work + 1;
+    const bool norm = (a.flags & SDR_FFT_NORM) != 0;
+    const int half = (a.flags & SDR_FFT_SHIFT) ? N2 / 2 : 0;
+    for (;;) {
+        __syncthreads();  // s_item and the exchange buffer are free again
+        if (tid == 0) s_item = (long long)atomicAdd(ticket, 1);
+        __syncthreads();
+        const long long item = s_item;
+        if (item >= total_items) break;
+        const long long g = item / (2 * S);
+        const int slot = (int)(item % (2 * S));
+        if (slot < S) {
+            // ------------------------------ STEP 0 ------------------------------
+            const long long b = g;
+            if (b >= a.batches) continue;
+            const int col0 = 16 * slot;
+            float2 v[16];
+            {
+                const int c = tid & 15, rr = tid >> 4;
+                const long long src = b * n + col0 + c + (long long)rr * N2;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = load_elem<FMT>(a.in, src + (long long)e * 16 * N2);
+                dft<16, 1>(v);
+                float2 *dst = sm + c * PL::SSTRIDE0;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) dst[pad(16 * rr + q)] = v[q];
+            }
+            __syncthreads();
+            {
+                const int col = tid >> 4, t = tid & 15;
+                const float2 *srcs = sm + col * PL::SSTRIDE0;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = srcs[pad(t + 16 * e)];
+#pragma unroll
+                for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw0[(q - 1) * 16 + t]);
+                dft<16, 1>(v);
+                float2 *dst = a.out + b * n + 256LL * (col0 + col) + t;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) dst[16 * q] = v[q];
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicAdd(flags + b, 1);
+        } else {
+            // ------------------------------ STEP 1 ------------------------------
+            const long long b = g - lag;
+            if (b < 0 || b >= a.batches) continue;
+            if (tid == 0)
+                while (ld_acquire_gpu(flags + b) < S) __nanosleep(64);
+            __syncthreads();
+            __threadfence();
+            const int c = tid % NC, t = tid / NC;
+            const int k = NC * (slot - S) + c;
+            float2 v[16];
+            {
+                const float2 *src = a.out + b * n + k + 256LL * t;
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = __ldcg(src + 256LL * TC * e);
+                // a_e = W_n^{k (t + e TC)} = w0 * ws^e
+                const float2 w0 = __ldg(a.tw + k * t), p1 = __ldg(a.tw + k * TC);
+                const float2 p2 = cmul(p1, p1), p4 = cmul(p2, p2), p8 = cmul(p4, p4);
+                float2 tw[16];
+                tw[0] = w0; tw[1] = cmul(w0, p1); tw[2] = cmul(w0, p2); tw[3] = cmul(tw[1], p2);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) tw[4 + e] = cmul(tw[e], p4);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) tw[8 + e] = cmul(tw[e], p8);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = cmul(v[e], tw[e]);
+            }
+            dft<16, 1>(v);
+            float2 *col = sm + c * PL::SSTRIDE1;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) col[pad(16 * t + q)] = v[q];
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = col[pad(t + e * TC)];
+#pragma unroll
+            for (int vi = 0; vi < NB2; ++vi) {
+                const int kk = (t + vi * TC) & 15;
+#pragma unroll
+                for (int q = 1; q < R2; ++q) v[vi + q * NB2] = cmul(v[vi + q * NB2], tw1[(q - 1) * 16 + kk]);
+            }
+#pragma unroll
+            for (int vi = 0; vi < NB2; ++vi) dft<R2, NB2>(v + vi);
+            float2 *ob = a.out + b * n + k;
+#pragma unroll
+            for (int vi = 0; vi < NB2; ++vi)
+#pragma unroll
+                for (int q = 0; q < R2; ++q) {
+                    const int k1 = (t + vi * TC) + 16 * q;  // bin k + 256 k1
+                    float2 o = v[vi + q * NB2];
+                    if (norm) { o.x *= a.norm; o.y *= a.norm; }
+                    ob[256LL * ((k1 + half) & (N2 - 1))] = o;
+                }
+        }
+    }
+}
+
+template <int LOGN2, int FMT>
+int launch_l2(const FftArgs &a, cudaStream_t st) {
+    using PL = L2Plan<LOGN2>;
+    const size_t smem = PL::smem_bytes();
+    auto kern = fft_l2_kernel<LOGN2, FMT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    if (per_sm < 1) per_sm = 1;
+    const long long resident = (long long)sms * per_sm;
+    // every resident CTA holds a STEP 0 (or older) ticket before the first STEP 1 item of a transform is reached
+    const int lag = (int)((resident * 3 / 2 + 2 * PL::S - 1) / (2 * PL::S)) + 1;
+    const long long total = (a.batches + lag) * 2 * PL::S;
+    e = cudaMemsetAsync(a.work, 0, (size_t)(a.batches + 1) * sizeof(int), st);
+    if (e != cudaSuccess) return cuda_status(e);
+    const long long ctas = total < resident ? total : resident;
+    kern<<<(unsigned)ctas, 256, smem, st>>>(a, lag, total);
+    count_launch();
+    return launch_status();
+}
+
 // ---- tiny sizes: direct DFT, one thread per output bin ---------------------------------------
 template <int FMT>
 __global__ void fft_naive_kernel(const void *in, float2 *out, const float2 *__restrict__ tw, long long batches,
@@ -590,6 +759,17 @@ int launch_big(const FftArgs &a, cudaStream_t st) {
     return launch_status();
 }
 
+// smallest log2 n that takes the L2-resident four-step kernel (tuning knob: SDR_FFT_L2_MIN=13 tries it for n = 8192)
+inline int l2_min_logn() {
+    static int v = 0;
+    if (!v) {
+        const char *e = std::getenv("SDR_FFT_L2_MIN");
+        v = e ? std::atoi(e) : 14;
+        if (v < 13) v = 13;
+    }
+    return v;
+}
+
 template <int FMT>
 int launch_fmt(const FftArgs &a, cudaStream_t st) {
     switch (a.log_n) {
@@ -606,10 +786,18 @@ int launch_fmt(const FftArgs &a, cudaStream_t st) {
             return launch_cta<10, FMT>(a, st);
         case 11: return launch_reg2<11, FMT>(a, st);
         case 12: return launch_reg2<12, FMT>(a, st);
-        case 13: return launch_reg2<13, FMT>(a, st);
-        case 14: return launch_cta<14, FMT>(a, st);
+        case 13:
+            if (a.work && !(a.flags & SDR_FFT_RFFT) && l2_min_logn() <= 13) return launch_l2<5, FMT>(a, st);
+            return launch_reg2<13, FMT>(a, st);
+        case 14:
+            if (a.work && !(a.flags & SDR_FFT_RFFT)) return launch_l2<6, FMT>(a, st);
+            return launch_cta<14, FMT>(a, st);
         case 15:
-        case 16: return launch_big<FMT>(a, st);
+            if (a.work && !(a.flags & SDR_FFT_RFFT)) return launch_l2<7, FMT>(a, st);
+            return launch_big<FMT>(a, st);
+        case 16:
+            if (a.work && !(a.flags & SDR_FFT_RFFT)) return launch_l2<8, FMT>(a, st);
+            return launch_big<FMT>(a, st);
     }
     return SDR_ERR_UNSUPPORTED;
 }

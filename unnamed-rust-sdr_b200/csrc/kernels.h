@@ -56,6 +56,7 @@ struct FftArgs {
     int fmt;            // sdr_format_t
     unsigned flags;     // SDR_FFT_*
     float norm;         // 1.0f / sqrtf((float)n)
+    int *work = nullptr; // n >= 2^14: batches + 1 ints of device scratch (ticket + per-transform counters), or null
 };
 int fft_pow2_launch(const FftArgs &a, cudaStream_t st);
 // direct O(n^2) DFT for tiny / odd sizes handled without Bluestein (n <= 64)
