@@ -553,7 +553,7 @@ __device__ __forceinline__ int ld_acquire_gpu(const int *p) {
 }
 
 template <int LOGN2, int FMT>
-__global__ void __launch_bounds__(256, 3) fft_l2_kernel(FftArgs a, int lag, long long total_items) {
+__global__ void __launch_bounds__(256, 4) fft_l2_kernel(FftArgs a, int lag, long long total_items) {
     using PL = L2Plan<LOGN2>;
     constexpr int N2 = PL::N2, NC = PL::NC, TC = PL::TC, R2 = PL::R2, NB2 = PL::NB2, S = PL::S;
     constexpr int n = 256 * N2;
@@ -568,9 +568,15 @@ __global__ void __launch_bounds__(256, 3) fft_l2_kernel(FftArgs a, int lag, long
     int *ticket = a.work, *flags = a.work + 1;
     const bool norm = (a.flags & SDR_FFT_NORM) != 0;
     const int half = (a.flags & SDR_FFT_SHIFT) ? N2 / 2 : 0;
+    // the next ticket is requested while the current item is processed (the atomic's round trip is off the critical path)
+    long long next = 0;
+    if (tid == 0) next = (long long)atomicAdd(ticket, 1);
     for (;;) {
         __syncthreads();  // s_item and the exchange buffer are free again
-        if (tid == 0) s_item = (long long)atomicAdd(ticket, 1);
+        if (tid == 0) {
+            s_item = next;
+            if (next < total_items) next = (long long)atomicAdd(ticket, 1);
+        }
         __syncthreads();
         const long long item = s_item;
         if (item >= total_items) break;
@@ -605,17 +611,18 @@ __global__ void __launch_bounds__(256, 3) fft_l2_kernel(FftArgs a, int lag, long
 #pragma unroll
                 for (int q = 0; q < 16; ++q) dst[16 * q] = v[q];
             }
-            __threadfence();
             __syncthreads();
-            if (tid == 0) atomicAdd(flags + b, 1);
+            if (tid == 0) {
+                __threadfence();  // cumulative: the whole CTA's stores (ordered before it by the barrier) are released
+                atomicAdd(flags + b, 1);
+            }
         } else {
             // ------------------------------ STEP 1 ------------------------------
             const long long b = g - lag;
             if (b < 0 || b >= a.batches) continue;
             if (tid == 0)
                 while (ld_acquire_gpu(flags + b) < S) __nanosleep(64);
-            __syncthreads();
-            __threadfence();
+            __syncthreads();  // the acquire above + this barrier order every thread's (L2, .cg) loads after the STEP 0 stores
             const int c = tid % NC, t = tid / NC;
             const int k = NC * (slot - S) + c;
             float2 v[16];

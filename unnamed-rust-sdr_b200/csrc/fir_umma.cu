@@ -54,7 +54,7 @@ struct UmArgs {
     int KS;              // k-steps of 32 bytes = 16 samples
     int delta;           // window start is `delta` samples left of the first needed sample (16-byte alignment)
     int ntiles;          // tiles per channel
-    int magic[2][3];     // [part][digit]: 0x4B400000 - 128 * sum of that column's digits
+    int magic[2][3];     // [part]: {-(256 C1 + C0), unused, 0x4B400000 - C2}, C_d = 128 * sum of that column's digit-d taps
     float sc[3];         // 2^-(S+7) * {1, 256, 65536}
 };
 
@@ -241,8 +241,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
         const int ew = warp - 2, g = ew >> 2;
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
         uint8_t *stg = gen + (size_t)UM_STAGES * UM_STAGE_BYTES + (size_t)KS * N * 32 + (size_t)ew * 32 * P * 8;
-        const float sc0 = a.sc[0], sc1 = a.sc[1], sc2 = a.sc[2];
-        const int mg[2][3] = {{a.magic[0][0], a.magic[0][1], a.magic[0][2]}, {a.magic[1][0], a.magic[1][1], a.magic[1][2]}};
+        const float sc0 = a.sc[0], sc2 = a.sc[2];
+        const int c10[2] = {a.magic[0][0], a.magic[1][0]}, m2[2] = {a.magic[0][2], a.magic[1][2]};
         uint32_t aph = 0;
         long long it = 0;
         for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
@@ -273,10 +273,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
                 float y[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    const float f0 = __int_as_float((int)d[0][i] + mg[i & 1][0]) - 12582912.0f;
-                    const float f1 = __int_as_float((int)d[1][i] + mg[i & 1][1]) - 12582912.0f;
-                    const float f2 = __int_as_float((int)d[2][i] + mg[i & 1][2]) - 12582912.0f;
-                    y[i] = fmaf(f2, sc2, fmaf(f1, sc1, f0 * sc0));
+                    // digits 0 and 1 combine exactly in s32 ((A1 << 8) + A0, |.| < 2^31 for K <= 511; wrap-around safe);
+                    // digit 2 (|A2| < 2^23) converts with the 1.5 * 2^23 magic add: one I2F per value, not three
+                    const float f10 = (float)((int)(d[1][i] << 8) + (int)d[0][i] + c10[i & 1]);
+                    const float f2 = __int_as_float((int)d[2][i] + m2[i & 1]) - 12582912.0f;
+                    y[i] = fmaf(f2, sc2, f10 * sc0);
                 }
                 if (pi == 3) {
                     // every accumulator of this set is in registers: hand the set back to the MMA warp
@@ -399,8 +400,14 @@ bool fir_umma_build_tables(const float *taps, int K, bool tc, int P, std::vector
         for (int dg = 0; dg < 3; ++dg) {
             long long s = 0;
             for (int k = 0; k < K; ++k) s += digit(k, part, 0, dg) + digit(k, part, 1, dg);
-            magic[part][dg] = (int)(0x4B400000LL - 128 * s);
+            magic[part][dg] = (int)(128 * s);  // C_d
         }
+    for (int part = 0; part < 2; ++part) {
+        const long long c10 = -(256LL * magic[part][1] + magic[part][0]);
+        magic[part][0] = (int)(unsigned)(unsigned long long)c10;  // two's complement wrap is what the kernel's s32 add expects
+        magic[part][1] = 0;
+        magic[part][2] = (int)(0x4B400000LL - magic[part][2]);
+    }
     const float base = std::ldexp(1.0f, -S - 7);
     sc[0] = base; sc[1] = base * 256.0f; sc[2] = base * 65536.0f;
     out.assign((size_t)8 * KS * N * 32, 0);
