@@ -26,6 +26,16 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np  # noqa: E402
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the `ncu --set full` captures
+# summarised under profiles/ (same command line as the bench, one launch).  null = not captured for that workload.
+NCU_TRAFFIC = {
+    "c2_fft1024_u8iq_2p28": (2.627e9, "profiles/r01_prof_fft_r01b.txt"),
+    "fir64_d1_u8iq_2p26": (6.124e8, "profiles/r01_prof_fir_umma_c1_v2.txt"),
+    "fir255_d1_u8iq_2p26": (6.122e8, "profiles/r01_prof_fir_umma_k255_v2.txt"),
+    "c5_fft65536_c64_2p27": (2.102e9, "profiles/r01_prof_fft_l2_64k_v1.txt"),
+}
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -118,7 +128,7 @@ def wl_fft1024_u8(torch, sdr, dev, log2_samples=28):
 
     return dict(name="c2_fft1024_u8iq_2p%d" % log2_samples, units=samples, bytes_per_unit=10.0, step=step,
                 e2e_setup=e2e_setup, e2e_step=e2e_step, h2d=2 * samples, d2h=8 * samples, cpu=cpu,
-                dtype="f32", kernel="fft_cta_kernel<10,u8iq>",
+                dtype="f32", kernel="fft1024_warp_kernel<u8iq>",
                 desc="batched 1024-pt FFT of u8 IQ, fused unpack + fftshift + 1/sqrt(N), %d transforms" % batches)
 
 
@@ -162,7 +172,8 @@ def wl_fir_u8(torch, sdr, dev, K=64, D=1, log2_samples=26, complex_taps=False):
 
     return dict(name="fir%d%s_d%d_u8iq_2p%d" % (K, "c" if complex_taps else "", D, log2_samples), units=samples,
                 bytes_per_unit=2.0 + 8.0 / D, step=step, e2e_setup=e2e_setup, e2e_step=e2e_step, h2d=2 * samples,
-                d2h=8 * n_out, cpu=cpu, dtype="f32", kernel="fir_rb_kernel" if D == 1 else "fir_generic_kernel",
+                d2h=8 * n_out, cpu=cpu, dtype="u8 x s8 -> s32 (tcgen05 kind::i8), f32 out" if (D == 1 and K <= 511) else "f16 mma.sync, f32 accumulate",
+                kernel="fir_umma_kernel (tcgen05/TMEM)" if (D == 1 and K <= 511) else "fir_mma_kernel (mma.sync)",
                 desc="fused u8-IQ unpack + %d-tap %s FIR, decimation %d" % (K, "complex" if complex_taps else "real", D))
 
 
@@ -420,7 +431,10 @@ def main():
                        "l2": "inputs+outputs per step exceed the 126 MB L2 (streamed from HBM every step)",
                        "parallelism": "independent shards per GPU, no data-path collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": wl["kernel"],
+                         "traffic": NCU_TRAFFIC.get(wl["name"], (None, None))[0],
+                         "traffic_source": NCU_TRAFFIC.get(wl["name"], (None, None))[1],
+                         "algorithmic_bytes": wl["units"] * wl["bytes_per_unit"],
+                         "peak_source": peak_src, "kernel": wl["kernel"],
                          "algorithmic_bytes_per_sample": wl["bytes_per_unit"]},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
         }
