@@ -142,13 +142,41 @@ def test_tensor_path_shapes(sdr, K, D, tc):
     iq = gen.random_u8(2 * n, 1000 + K + D)
     x = O.unpack_u8iq(iq)
     truth = O.fir_f64(taps, x)[D - 1::D]
-    for flags in ((0, NO_TCGEN05) if D == 1 else (0,)):
+    for flags in (0, NO_TCGEN05):
         f = sdr.Fir(taps, "u8iq", decimation=D, flags=flags)
         a = f.process(iq[:2 * 777])
         b = f.process(iq[2 * 777:])
         got = np.concatenate([a, b])
-        assert f.last_path == (4 if (D == 1 and K <= 511 and flags == 0) else 3)
+        assert f.last_path == (4 if (K <= 511 and flags == 0) else 3)
         assert len(got) == n // D and rel_err(got, truth) < TOL
+
+
+@pytest.mark.parametrize("D", [2, 3, 4, 5, 6, 7, 10, 12, 20, 50, 8, 16, 96])
+@pytest.mark.parametrize("K,tc", [(64, True), (255, False)])
+def test_tcgen05_decimating_path(sdr, D, K, tc):
+    """Decimate fused behind the filter on the tensor cores: rows stay 32 samples apart, only the offsets a kept
+    output can take (multiples of gcd(D, 32)) get columns.  Exact integer sums: any blocking gives the same bits."""
+    import math
+    rng = np.random.default_rng(K * 3 + D)
+    taps = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+    if tc:
+        taps = (taps + 1j * rng.standard_normal(K) / np.sqrt(K)).astype(np.complex64)
+    n = 5 * 8192 + 37
+    iq = gen.random_u8(2 * n, 500 + D)
+    truth = O.fir_f64(taps, O.unpack_u8iq(iq))[D - 1::D]
+    f = sdr.Fir(taps, "u8iq", decimation=D)
+    whole = f.process(iq)
+    if math.gcd(D, 32) <= 4:
+        assert f.last_path == 4
+    else:
+        assert f.last_path in (1, 3)  # D = 8, 16, 96: too few candidates per row for the tcgen05 path
+    assert len(whole) == n // D and rel_err(whole, truth) < (1e-6 if f.last_path == 4 else TOL)
+    if f.last_path != 4:
+        return
+    f.reset()
+    cuts = [0, 1, D, D + 1, 8192, 8192 + 3, 3 * 8192 - 1, n]
+    parts = np.concatenate([f.process(iq[2 * a:2 * b]) for a, b in zip(cuts[:-1], cuts[1:])])
+    assert np.array_equal(parts.view(np.uint32), whole.view(np.uint32))
 
 
 @pytest.mark.parametrize("P", [8, 16, 32])

@@ -22,6 +22,12 @@
 //     two FFMAs: the result is the exactly-accumulated dot product rounded ~once -- closer to the f64 truth than the
 //     reference's own sequential f32 sum (tests/test_gpu_fir.py bars: 1e-5 relative, and <= 4x the reference's error).
 //
+// Decimation (signal::Decimate fused behind the filter, src/signal/adapters/mod.rs:30-37): rows stay R = 32 samples
+// apart (a matrix descriptor cannot step by D), and the B columns are the CANDIDATE offsets inside a row at which a
+// kept output can fall: kept output m sits D*m samples after output 0, i.e. in row (D m) div R at offset (D m) mod R, a
+// multiple of g = gcd(D, R).  Only those R/g offsets get columns (D = 10: 16 of 32, N = 96), the epilogue converts and
+// stores the ones that are kept outputs (compare against a running "next kept position", no division per candidate).
+//
 // Warp roles (one persistent CTA per SM, 320 threads):
 //   warp 0      producer: cp.async 16-byte chunks global -> (swizzled) stage, completion on an mbarrier
 //                          (cp.async.mbarrier.arrive.noinc); history / zero padding at the stream start by plain stores
@@ -42,9 +48,7 @@ namespace sdr {
 namespace {
 
 constexpr int UM_STAGES = 4;
-constexpr int UM_STAGE_BYTES = 10240;  // 8 KB of window starts per tile + (KS*32 B) halo; multiple of 1024 (swizzle period)
-constexpr int UM_TILE_OUT = 4096;      // outputs per tile = 128 * MB * P
-constexpr int UM_ACC_COLS = 192;       // TMEM columns per accumulator set = MB * 6P
+constexpr int UM_ACC_COLS = 192;       // TMEM columns per accumulator set = MB * 6 PC
 constexpr int UM_THREADS = 320;
 constexpr int UM_MAX_K = 511;
 
@@ -54,6 +58,8 @@ struct UmArgs {
     int KS;              // k-steps of 32 bytes = 16 samples
     int delta;           // window start is `delta` samples left of the first needed sample (16-byte alignment)
     int ntiles;          // tiles per channel
+    int stage_bytes;     // one stage: the tile's window starts + (KS*32 B) halo, multiple of 1024 (swizzle period)
+    long long n_rows;    // window rows per channel that hold at least one kept output
     int magic[2][3];     // [part]: {-(256 C1 + C0), unused, 0x4B400000 - C2}, C_d = 128 * sum of that column's digit-d taps
     float sc[3];         // 2^-(S+7) * {1, 256, 65536}
 };
@@ -107,17 +113,26 @@ template <> struct UmLayout<8>  { static constexpr uint32_t type = 0; __device__
 template <> struct UmLayout<16> { static constexpr uint32_t type = 6; __device__ static uint32_t swz(uint32_t o) { return o ^ (((o >> 7) & 1u) << 4); } };
 template <> struct UmLayout<32> { static constexpr uint32_t type = 4; __device__ static uint32_t swz(uint32_t o) { return o ^ (((o >> 7) & 3u) << 4); } };
 
-__host__ __device__ constexpr size_t um_smem_bytes(int P, int KS) {
-    // tables + stages + epilogue staging (8 warps x 32 rows x P*8 B) + 1 KB alignment slack + barriers
-    return (size_t)KS * 6 * P * 32 + (size_t)UM_STAGES * UM_STAGE_BYTES + (size_t)8 * 32 * P * 8 + 1024 + 256;
+// one stage holds the 128*MB window starts of a tile, R samples apart, plus the KS*32-byte halo of the last row
+__host__ __device__ constexpr int um_stage_bytes(int R, int PC, int KS) {
+    return (2 * R * (128 * (32 / PC) - 1) + 32 * KS + 1023) / 1024 * 1024;
+}
+__host__ __device__ constexpr size_t um_smem_bytes(int R, int PC, int KS, bool dec) {
+    // tables + stages + epilogue staging (D == 1: 8 warps x 32 rows x R*8 B) + 1 KB alignment slack + barriers
+    return (size_t)KS * 6 * PC * 32 + (size_t)UM_STAGES * um_stage_bytes(R, PC, KS) + (dec ? 0 : (size_t)8 * 32 * R * 8) + 1024 + 256;
 }
 
-template <int P>
+// R = samples between window rows (8 / 16 / 32: no / 32-byte / 64-byte swizzle), PC = output candidates per row
+// (PC == R when D == 1), DEC = decimating epilogue.
+template <int R, int PC, bool DEC>
 __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a) {
-    constexpr int MB = 32 / P;               // 128-row blocks per tile
-    constexpr int N = 6 * P;                 // MMA N: 3 digits x P phases x (I, Q)
-    constexpr int ROWB = 2 * P;              // bytes between window rows
+    constexpr int P = R;                     // (name kept from the D == 1 derivation: outputs per row when PC == R)
+    constexpr int MB = 32 / PC;              // 128-row blocks per tile
+    constexpr int N = 6 * PC;                // MMA N: 3 digits x PC candidates x (I, Q)
+    constexpr int ROWB = 2 * R;              // bytes between window rows
     constexpr int CPR = P / 2;               // 16-byte chunks per staged output row (P complex f32)
+    constexpr int TILE_ROWS = 128 * MB;
+    const int SB = a.stage_bytes;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * UM_STAGES + 4];
     __shared__ uint32_t tmem_base_s;
@@ -126,7 +141,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
     const int KS = a.KS;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // stages first: 1024-aligned for the swizzle modes
     const uint32_t stage0 = base;
-    const uint32_t tab_s = stage0 + UM_STAGES * UM_STAGE_BYTES;
+    const uint32_t tab_s = stage0 + UM_STAGES * SB;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));        // generic pointer to `base`
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -137,7 +152,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
     // ---- one-time setup ----
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.tab);
-        uint4 *dst = reinterpret_cast<uint4 *>(gen + UM_STAGES * UM_STAGE_BYTES);
+        uint4 *dst = reinterpret_cast<uint4 *>(gen + UM_STAGES * SB);
         for (int i = tid; i < KS * N * 2; i += UM_THREADS) dst[i] = __ldg(src + i);
     }
     if (tid == 0) {
@@ -165,12 +180,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
         uint32_t ph = 0;
         for (long long w = blockIdx.x; w < nwork; w += wstride) {
             const int ch = (int)(w / a.ntiles);
-            const long long m0 = (w % a.ntiles) * UM_TILE_OUT;
-            const long long w0 = f.first + m0 - (f.K - 1) - a.delta;  // multiple of 8 samples
+            const long long w0 = f.first - (f.K - 1) - a.delta + (w % a.ntiles) * (long long)(TILE_ROWS * R);  // multiple of 8
             const unsigned char *in = (const unsigned char *)f.in + (long long)ch * f.in_stride * 2;
             const unsigned char *hist = (const unsigned char *)f.hist + (long long)ch * f.hist_stride * 2;
             mbar_wait(empty_bar(stage), ph ^ 1u);
-            const uint32_t sbase = stage0 + (uint32_t)stage * UM_STAGE_BYTES;
+            const uint32_t sbase = stage0 + (uint32_t)stage * SB;
             bool slow = false;
             if (w0 >= 0 && w0 + 8LL * nchunks <= f.n_in) {
                 // interior tile (all but the first / last of a block): nothing but address arithmetic and LDGSTS
@@ -198,7 +212,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
                         uint4 q;
                         q.x = h[0] | ((unsigned)h[1] << 16); q.y = h[2] | ((unsigned)h[3] << 16);
                         q.z = h[4] | ((unsigned)h[5] << 16); q.w = h[6] | ((unsigned)h[7] << 16);
-                        *reinterpret_cast<uint4 *>(gen + (size_t)stage * UM_STAGE_BYTES + off) = q;
+                        *reinterpret_cast<uint4 *>(gen + (size_t)stage * SB + off) = q;
                         slow = true;
                     }
                     // chunks entirely past the end feed only rows whose outputs are never stored: left as they are
@@ -220,7 +234,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
             mbar_wait(acce_bar(as), aph ^ 1u);
             tc_fence_after();
             if (lane == 0) {
-                const uint64_t adesc0 = smem_desc(stage0 + (uint32_t)stage * UM_STAGE_BYTES, 16, 8 * ROWB, UmLayout<P>::type);
+                const uint64_t adesc0 = smem_desc(stage0 + (uint32_t)stage * SB, 16, 8 * ROWB, UmLayout<P>::type);
                 const uint32_t d0 = tmem + (uint32_t)(as * UM_ACC_COLS);
                 for (int kk = 0; kk < KS; ++kk) {
                     const uint64_t bd = bdesc0 + (uint64_t)((kk * N * 32) >> 4);
@@ -240,7 +254,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
         // ================= epilogue: warpgroup g owns accumulator set g =================
         const int ew = warp - 2, g = ew >> 2;
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-        uint8_t *stg = gen + (size_t)UM_STAGES * UM_STAGE_BYTES + (size_t)KS * N * 32 + (size_t)ew * 32 * P * 8;
+        uint8_t *stg = gen + (size_t)UM_STAGES * SB + (size_t)KS * N * 32 + (size_t)ew * 32 * P * 8;
         const float sc0 = a.sc[0], sc2 = a.sc[2];
         const int c10[2] = {a.magic[0][0], a.magic[1][0]}, m2[2] = {a.magic[0][2], a.magic[1][2]};
         uint32_t aph = 0;
@@ -248,20 +262,23 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
         for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
             if ((it & 1) != g) continue;
             const int ch = (int)(w / a.ntiles);
-            const long long m0 = (w % a.ntiles) * UM_TILE_OUT;
+            const long long row0 = (w % a.ntiles) * (long long)TILE_ROWS;  // first window row of the tile
+            const long long m0 = row0 * P;                                    // D == 1: its first output
             float2 *out = (float2 *)f.out + (long long)ch * f.out_stride;
             mbar_wait(accf_bar(g), aph);
             tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * UM_ACC_COLS);
             // 4 pieces per tile (MB * P/8 == 4): piece = 8 phases of one 128-row block = 16 columns of each digit.
             // The TMEM loads of piece i+1 are in flight while piece i is converted and staged.
-            constexpr int PPB = P / 8;  // pieces per 128-row block
+            constexpr int PPB = PC / 8;  // pieces per 128-row block
             uint32_t v[2][3][16];
+            long long mk = 0;  // DEC: next kept output of this lane's row
+            int nv = -1;       // DEC: its offset inside the row
             auto issue = [&](int pi, uint32_t (&d)[3][16]) {
                 const uint32_t col = tbase + (uint32_t)((pi / PPB) * N + 16 * (pi % PPB));
                 tmem_ld16(col, d[0]);
-                tmem_ld16(col + 2 * P, d[1]);
-                tmem_ld16(col + 4 * P, d[2]);
+                tmem_ld16(col + 2 * PC, d[1]);
+                tmem_ld16(col + 4 * PC, d[2]);
             };
             issue(0, v[0]);
 #pragma unroll
@@ -270,53 +287,73 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
                 tmem_ld_wait();
                 if (pi + 1 < 4) issue(pi + 1, v[(pi + 1) & 1]);
                 uint32_t (&d)[3][16] = v[pi & 1];
-                float y[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
+                auto value = [&](int i) -> float {
                     // digits 0 and 1 combine exactly in s32 ((A1 << 8) + A0, |.| < 2^31 for K <= 511; wrap-around safe);
                     // digit 2 (|A2| < 2^23) converts with the 1.5 * 2^23 magic add: one I2F per value, not three
                     const float f10 = (float)((int)(d[1][i] << 8) + (int)d[0][i] + c10[i & 1]);
                     const float f2 = __int_as_float((int)d[2][i] + m2[i & 1]) - 12582912.0f;
-                    y[i] = fmaf(f2, sc2, f10 * sc0);
-                }
+                    return fmaf(f2, sc2, f10 * sc0);
+                };
                 if (pi == 3) {
                     // every accumulator of this set is in registers: hand the set back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acce_bar(g));
                 }
-                // row `lane` of the warp's staging tile, chunks 4pc .. 4pc+3, XOR-swizzled: conflict-free both ways
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int c = 4 * pc + q;
-                    const int pcn = (P == 8) ? (c ^ ((lane >> 1) & 3)) : (c ^ (lane & 7));
-                    *reinterpret_cast<float4 *>(stg + ((size_t)lane * CPR + pcn) * 16) =
-                        make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-                }
-                if (pc == PPB - 1) {
-                    __syncwarp();
-                    // the warp's 32 rows are 32*P consecutive outputs: 512 contiguous bytes per store instruction
-                    const long long mrow = m0 + (long long)(mb * 128 + quad * 32) * P;
-                    float4 val[CPR];
-#pragma unroll
-                    for (int i = 0; i < CPR; ++i) {
-                        const int q = i * 32 + lane;
-                        const int row = q / CPR, c = q % CPR;
-                        const int pcn = (P == 8) ? (c ^ ((row >> 1) & 3)) : (c ^ (row & 7));
-                        val[i] = *reinterpret_cast<const float4 *>(stg + ((size_t)row * CPR + pcn) * 16);
+                if constexpr (DEC) {
+                    // candidates 8pc .. 8pc+7 of window row `row`: offset g*u inside the row is a kept output iff it
+                    // equals the running next kept position (row-relative); at most one division per row
+                    constexpr int G = R / PC;
+                    const long long row = row0 + mb * 128 + quad * 32 + lane;
+                    if (pc == 0) {
+                        mk = (row * R + f.D - 1) / f.D;            // first kept output at or after the row start
+                        nv = (int)(mk * f.D - row * R);            // its offset inside the row (may be >= R: none)
                     }
-                    if (mrow + 32 * P <= f.n_out) {
 #pragma unroll
-                        for (int i = 0; i < CPR; ++i) *reinterpret_cast<float4 *>(out + mrow + 2 * (i * 32 + lane)) = val[i];
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < CPR; ++i) {
-                            const long long m = mrow + 2LL * (i * 32 + lane);
-                            if (m + 1 < f.n_out) *reinterpret_cast<float4 *>(out + m) = val[i];
-                            else if (m < f.n_out) out[m] = make_float2(val[i].x, val[i].y);
+                    for (int u = 0; u < 8; ++u) {
+                        if (G * (8 * pc + u) == nv) {
+                            if (mk < f.n_out) out[mk] = make_float2(value(2 * u), value(2 * u + 1));
+                            ++mk;
+                            nv += f.D;
                         }
                     }
-                    __syncwarp();
+                } else {
+                    float y[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) y[i] = value(i);
+                    // row `lane` of the warp's staging tile, chunks 4pc .. 4pc+3, XOR-swizzled: conflict-free both ways
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int c = 4 * pc + q;
+                        const int pcn = (P == 8) ? (c ^ ((lane >> 1) & 3)) : (c ^ (lane & 7));
+                        *reinterpret_cast<float4 *>(stg + ((size_t)lane * CPR + pcn) * 16) =
+                            make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                    }
+                    if (pc == PPB - 1) {
+                        __syncwarp();
+                        // the warp's 32 rows are 32*P consecutive outputs: 512 contiguous bytes per store instruction
+                        const long long mrow = m0 + (long long)(mb * 128 + quad * 32) * P;
+                        float4 val[CPR];
+#pragma unroll
+                        for (int i = 0; i < CPR; ++i) {
+                            const int q = i * 32 + lane;
+                            const int row = q / CPR, c = q % CPR;
+                            const int pcn = (P == 8) ? (c ^ ((row >> 1) & 3)) : (c ^ (row & 7));
+                            val[i] = *reinterpret_cast<const float4 *>(stg + ((size_t)row * CPR + pcn) * 16);
+                        }
+                        if (mrow + 32 * P <= f.n_out) {
+#pragma unroll
+                            for (int i = 0; i < CPR; ++i) *reinterpret_cast<float4 *>(out + mrow + 2 * (i * 32 + lane)) = val[i];
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < CPR; ++i) {
+                                const long long m = mrow + 2LL * (i * 32 + lane);
+                                if (m + 1 < f.n_out) *reinterpret_cast<float4 *>(out + m) = val[i];
+                                else if (m < f.n_out) out[m] = make_float2(val[i].x, val[i].y);
+                            }
+                        }
+                        __syncwarp();
+                    }
                 }
             }
             aph ^= 1u;
@@ -344,30 +381,45 @@ inline bool digits3(long long t, int d[3]) {
 
 }  // namespace
 
-int fir_umma_ksteps(int K, int P) { return (K + P + 6 + 15) / 16; }
+static int gcd_i(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
 
-int fir_umma_pick_p(int K) {
-    if (const char *e = std::getenv("SDR_UMMA_P")) {
-        const int p = std::atoi(e);
-        if (p == 8 || p == 16 || p == 32) return p;
+// k-steps of 16 samples: a row's window spans K + 7 (alignment) + the largest candidate offset R - g samples
+int fir_umma_ksteps(int K, int R, int PC) { return (K + 7 + R - R / PC + 15) / 16; }
+
+// geometry for (K, D): row pitch R and candidates per row PC; false if the tcgen05 path does not apply
+bool fir_umma_geometry(int K, int D, int *R_out, int *PC_out) {
+    if (K < 1 || K > UM_MAX_K || D < 1) return false;
+    if (D == 1) {
+        int best = 0;
+        double best_c = 1e30;
+        const char *e = std::getenv("SDR_UMMA_P");
+        const int forced = e ? std::atoi(e) : 0;
+        for (int p : {8, 16, 32}) {
+            const int ks = fir_umma_ksteps(K, p, p);
+            if (um_smem_bytes(p, p, ks, false) > 220 * 1024) continue;
+            // cycles per output ~ KS * max(45, N/2) / (128 P): wide rows amortise the band padding
+            const double c = (forced == p) ? 0.0 : ks * std::max(45.0, 3.0 * p) / (128.0 * p);
+            if (c < best_c) { best_c = c; best = p; }
+        }
+        if (!best) return false;
+        *R_out = *PC_out = best;
+        return true;
     }
-    // cycles per output ~ KS(P) * max(45, (4096 + 192 P) / 128) / (128 P): wide rows amortise the window reads
-    int best = 8;
-    double best_c = 1e30;
-    for (int p : {8, 16, 32}) {
-        const int ks = fir_umma_ksteps(K, p);
-        if (um_smem_bytes(p, ks) > 220 * 1024 || 32 * ks + 8192 - 2 * p > UM_STAGE_BYTES) continue;
-        const double c = ks * std::max(45.0, (4096.0 + 192.0 * p) / 128.0) / (128.0 * p);
-        if (c < best_c) { best_c = c; best = p; }
-    }
-    return best;
+    const int g = gcd_i(D, 32);
+    if (g > 4) return false;  // fewer than 8 candidates per 32-sample row: N would drop below the M = 128 minimum of 16
+    const int ks = fir_umma_ksteps(K, 32, 32 / g);
+    if (um_smem_bytes(32, 32 / g, ks, true) > 220 * 1024) return false;
+    *R_out = 32;
+    *PC_out = 32 / g;
+    return true;
 }
 
 // host: the 8 alignment variants of the Toeplitz tap table.  Layout [delta][kk][canonical N x 32 B block]:
 // element (n, kb) of a block sits at (n/8)*256 + (kb/16)*128 + (n%8)*16 + kb%16 (no-swizzle K-major core matrices).
-bool fir_umma_build_tables(const float *taps, int K, bool tc, int P, std::vector<uint8_t> &out, int magic[2][3], float sc[3]) {
+// Column n = digit * 2 PC + 2 u + part; candidate u is the output whose oldest sample sits g*u (+ delta) into the row.
+bool fir_umma_build_tables(const float *taps, int K, bool tc, int R, int PC, std::vector<uint8_t> &out, int magic[2][3], float sc[3]) {
     if (K < 1 || K > UM_MAX_K) return false;
-    const int KS = fir_umma_ksteps(K, P), N = 6 * P, W = tc ? 2 : 1;
+    const int KS = fir_umma_ksteps(K, R, PC), N = 6 * PC, W = tc ? 2 : 1, G = R / PC;
     float cmax = 0.0f;
     for (int i = 0; i < K * W; ++i) {
         if (!std::isfinite(taps[i])) return false;
@@ -415,10 +467,10 @@ bool fir_umma_build_tables(const float *taps, int K, bool tc, int P, std::vector
         for (int kk = 0; kk < KS; ++kk) {
             uint8_t *blk = out.data() + ((size_t)delta * KS + kk) * N * 32;
             for (int n = 0; n < N; ++n) {
-                const int dg = n / (2 * P), j = (n % (2 * P)) / 2, part = n & 1;
+                const int dg = n / (2 * PC), u = (n % (2 * PC)) / 2, part = n & 1;
                 for (int kb = 0; kb < 32; ++kb) {
                     const int s = kk * 16 + kb / 2, q = kb & 1;
-                    const int k = K - 1 + delta + j - s;
+                    const int k = K - 1 + delta + G * u - s;
                     int v = 0;
                     if (k >= 0 && k < K) v = digit(k, part, q, dg);
                     blk[(n / 8) * 256 + (kb / 16) * 128 + (n % 8) * 16 + kb % 16] = (uint8_t)(int8_t)v;
@@ -429,22 +481,26 @@ bool fir_umma_build_tables(const float *taps, int K, bool tc, int P, std::vector
 }
 
 // returns SDR_ERR_UNSUPPORTED when this path does not apply (caller falls back to the mma.sync / CUDA-core kernels)
-int fir_umma_launch(const FirArgs &f, int P, const uint8_t *d_tables, const int magic[2][3], const float sc[3], cudaStream_t st) {
+int fir_umma_launch(const FirArgs &f, int R, int PC, const uint8_t *d_tables, const int magic[2][3], const float sc[3], cudaStream_t st) {
     if (f.n_out <= 0) return SDR_OK;
-    if (f.D != 1 || f.K > UM_MAX_K) return SDR_ERR_UNSUPPORTED;
+    if (f.K > UM_MAX_K || (f.D == 1 && R != PC) || (f.D != 1 && R != 32)) return SDR_ERR_UNSUPPORTED;
     if (((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 15) || (f.out_stride & 1) || (f.in_stride & 7) || ((uintptr_t)f.hist & 1))
         return SDR_ERR_UNSUPPORTED;
-    const int KS = fir_umma_ksteps(f.K, P);
-    const size_t smem = um_smem_bytes(P, KS);
-    if (smem > 220 * 1024 || 32 * KS + 8192 - 2 * P > UM_STAGE_BYTES) return SDR_ERR_UNSUPPORTED;
+    const bool dec = f.D != 1;
+    const int KS = fir_umma_ksteps(f.K, R, PC);
+    const size_t smem = um_smem_bytes(R, PC, KS, dec);
+    if (smem > 220 * 1024) return SDR_ERR_UNSUPPORTED;
     UmArgs a;
     a.f = f;
     a.KS = KS;
     long long d = (f.first - (f.K - 1)) % 8;
     if (d < 0) d += 8;
     a.delta = (int)d;
-    a.tab = d_tables + (size_t)d * KS * 6 * P * 32;
-    a.ntiles = (int)((f.n_out + UM_TILE_OUT - 1) / UM_TILE_OUT);
+    a.tab = d_tables + (size_t)d * KS * 6 * PC * 32;
+    a.stage_bytes = um_stage_bytes(R, PC, KS);
+    a.n_rows = ((f.n_out - 1) * (long long)f.D) / R + 1;
+    const int tile_rows = 128 * (32 / PC);
+    a.ntiles = (int)((a.n_rows + tile_rows - 1) / tile_rows);
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 3; ++j) a.magic[i][j] = magic[i][j];
     for (int j = 0; j < 3; ++j) a.sc[j] = sc[j];
@@ -463,10 +519,18 @@ int fir_umma_launch(const FirArgs &f, int P, const uint8_t *d_tables, const int 
         count_launch();
         return launch_status();
     };
-    switch (P) {
-        case 8: return go(fir_umma_kernel<8>);
-        case 16: return go(fir_umma_kernel<16>);
-        case 32: return go(fir_umma_kernel<32>);
+    if (!dec) {
+        switch (R) {
+            case 8: return go(fir_umma_kernel<8, 8, false>);
+            case 16: return go(fir_umma_kernel<16, 16, false>);
+            case 32: return go(fir_umma_kernel<32, 32, false>);
+        }
+    } else if (R == 32) {
+        switch (PC) {
+            case 8: return go(fir_umma_kernel<32, 8, true>);
+            case 16: return go(fir_umma_kernel<32, 16, true>);
+            case 32: return go(fir_umma_kernel<32, 32, true>);
+        }
     }
     return SDR_ERR_UNSUPPORTED;
 }

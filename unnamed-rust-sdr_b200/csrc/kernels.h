@@ -36,12 +36,13 @@ float fir_tc_build_tables(const float *taps, int K, bool taps_complex, int D, st
 // SDR_ERR_UNSUPPORTED = the tensor path does not apply to this call (alignment / shared-memory budget)
 int fir_tc_launch(const FirArgs &a, bool taps_complex, const uint2 *d_tables, float out_scale, cudaStream_t st);
 
-// tcgen05 / TMEM Toeplitz FIR for u8 IQ input, D == 1 (fir_umma.cu).  P = outputs per window row (8, 16, 32).
-int fir_umma_ksteps(int K, int P);
-int fir_umma_pick_p(int K);
-bool fir_umma_build_tables(const float *taps, int K, bool taps_complex, int P, std::vector<uint8_t> &out,
+// tcgen05 / TMEM Toeplitz FIR (+ Decimate) for u8 IQ input (fir_umma.cu).  R = samples between window rows,
+// PC = output candidates per row (== R when D == 1).
+int fir_umma_ksteps(int K, int R, int PC);
+bool fir_umma_geometry(int K, int D, int *R, int *PC);
+bool fir_umma_build_tables(const float *taps, int K, bool taps_complex, int R, int PC, std::vector<uint8_t> &out,
                            int magic[2][3], float sc[3]);
-int fir_umma_launch(const FirArgs &a, int P, const uint8_t *d_tables, const int magic[2][3], const float sc[3],
+int fir_umma_launch(const FirArgs &a, int R, int PC, const uint8_t *d_tables, const int magic[2][3], const float sc[3],
                     cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------
