@@ -172,8 +172,7 @@ def wl_fir_u8(torch, sdr, dev, K=64, D=1, log2_samples=26, complex_taps=False):
 
     return dict(name="fir%d%s_d%d_u8iq_2p%d" % (K, "c" if complex_taps else "", D, log2_samples), units=samples,
                 bytes_per_unit=2.0 + 8.0 / D, step=step, e2e_setup=e2e_setup, e2e_step=e2e_step, h2d=2 * samples,
-                d2h=8 * n_out, cpu=cpu, dtype="u8 x s8 -> s32 (tcgen05 kind::i8), f32 out" if (D == 1 and K <= 511) else "f16 mma.sync, f32 accumulate",
-                kernel="fir_umma_kernel (tcgen05/TMEM)" if (D == 1 and K <= 511) else "fir_mma_kernel (mma.sync)",
+                d2h=8 * n_out, cpu=cpu, dtype="u8 x s8 -> s32 (tcgen05 kind::i8), f32 out", kernel="fir_umma_kernel (tcgen05/TMEM)",
                 desc="fused u8-IQ unpack + %d-tap %s FIR, decimation %d" % (K, "complex" if complex_taps else "real", D))
 
 

@@ -86,6 +86,8 @@ int main() {
     run<256, 1, 8>("sw64", 64, 4, dc); run<256, 2, 8>("sw64", 64, 4, dc);
     run<128, 1, 8>("sw64", 64, 4, dc); run<128, 2, 8>("sw64", 64, 4, dc); run<128, 4, 8>("sw64", 64, 4, dc);
     run<64, 4, 8>("none", 16, 0, dc);
+    run<96, 2, 19>("sw64", 64, 4, dc); run<96, 1, 19>("sw64", 64, 4, dc); run<48, 4, 19>("sw64", 64, 4, dc); run<192, 1, 19>("sw64", 64, 4, dc);
+    run<96, 2, 19>("sw32", 32, 6, dc);
     printf("rate probe done\n");
     return 0;
 }

@@ -47,9 +47,12 @@ namespace sdr {
 
 namespace {
 
-constexpr int UM_STAGES = 4;
+constexpr int UM_STAGES = 4;            // at most; fewer when the tap tables leave less shared memory
 constexpr int UM_ACC_COLS = 192;       // TMEM columns per accumulator set = MB * 6 PC
-constexpr int UM_THREADS = 320;
+constexpr int UM_PROD_WARPS = 3;                   // producer warps (one was LDGSTS-issue bound: 8-10 B/cycle/SM)
+constexpr int UM_MMA_WARP = UM_PROD_WARPS;         // the MMA-issuing warp
+constexpr int UM_EPI_WARP0 = UM_PROD_WARPS + 1;    // 16 epilogue warps follow
+constexpr int UM_THREADS = (UM_PROD_WARPS + 1 + 16) * 32;
 constexpr int UM_MAX_K = 511;
 
 struct UmArgs {
@@ -60,6 +63,7 @@ struct UmArgs {
     int ntiles;          // tiles per channel
     int stage_bytes;     // one stage: the tile's window starts + (KS*32 B) halo, multiple of 1024 (swizzle period)
     long long n_rows;    // window rows per channel that hold at least one kept output
+    int stages;          // input stages in the ring (2..UM_STAGES)
     int magic[2][3];     // [part]: {-(256 C1 + C0), unused, 0x4B400000 - C2}, C_d = 128 * sum of that column's digit-d taps
     float sc[3];         // 2^-(S+7) * {1, 256, 65536}
 };
@@ -117,9 +121,9 @@ template <> struct UmLayout<32> { static constexpr uint32_t type = 4; __device__
 __host__ __device__ constexpr int um_stage_bytes(int R, int PC, int KS) {
     return (2 * R * (128 * (32 / PC) - 1) + 32 * KS + 1023) / 1024 * 1024;
 }
-__host__ __device__ constexpr size_t um_smem_bytes(int R, int PC, int KS, bool dec) {
-    // tables + stages + epilogue staging (D == 1: 8 warps x 32 rows x R*8 B) + 1 KB alignment slack + barriers
-    return (size_t)KS * 6 * PC * 32 + (size_t)UM_STAGES * um_stage_bytes(R, PC, KS) + (dec ? 0 : (size_t)8 * 32 * R * 8) + 1024 + 256;
+__host__ __device__ constexpr size_t um_smem_bytes(int R, int PC, int KS, bool dec, int stages = UM_STAGES) {
+    // tables + stages + epilogue staging (16 warps x 32 rows x 64 / 128 B; decimating: x 192 B) + 1 KB slack + barriers
+    return (size_t)KS * 6 * PC * 32 + (size_t)stages * um_stage_bytes(R, PC, KS) + (dec ? (size_t)16 * 6144 : (size_t)16 * 32 * (R >= 16 ? 8 : 4) * 16) + 1024 + 256;
 }
 
 // R = samples between window rows (8 / 16 / 32: no / 32-byte / 64-byte swizzle), PC = output candidates per row
@@ -130,9 +134,8 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
     constexpr int MB = 32 / PC;              // 128-row blocks per tile
     constexpr int N = 6 * PC;                // MMA N: 3 digits x PC candidates x (I, Q)
     constexpr int ROWB = 2 * R;              // bytes between window rows
-    constexpr int CPR = P / 2;               // 16-byte chunks per staged output row (P complex f32)
     constexpr int TILE_ROWS = 128 * MB;
-    const int SB = a.stage_bytes;
+    const int SB = a.stage_bytes, NST = a.stages;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * UM_STAGES + 4];
     __shared__ uint32_t tmem_base_s;
@@ -141,7 +144,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
     const int KS = a.KS;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // stages first: 1024-aligned for the swizzle modes
     const uint32_t stage0 = base;
-    const uint32_t tab_s = stage0 + UM_STAGES * SB;
+    const uint32_t tab_s = stage0 + NST * SB;
     uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));        // generic pointer to `base`
     const uint32_t bar0 = smem_u32(bars);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -152,15 +155,15 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
     // ---- one-time setup ----
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.tab);
-        uint4 *dst = reinterpret_cast<uint4 *>(gen + UM_STAGES * SB);
+        uint4 *dst = reinterpret_cast<uint4 *>(gen + NST * SB);
         for (int i = tid; i < KS * N * 2; i += UM_THREADS) dst[i] = __ldg(src + i);
     }
     if (tid == 0) {
-        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full_bar(s), 32); mbar_init(empty_bar(s), 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 4); }
+        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full_bar(s), 32 * UM_PROD_WARPS); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {
+    if (warp == UM_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -173,8 +176,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
     const long long nwork = (long long)a.ntiles * f.n_ch;
     const long long wstride = gridDim.x;
 
-    if (warp == 0) {
-        // ================= producer =================
+    if (warp < UM_PROD_WARPS) {
+        // ================= producers =================
+        const int ptid = warp * 32 + lane;
         const int nchunks = (ROWB * (128 * MB - 1) + 32 * KS + 15) / 16;
         int stage = 0;
         uint32_t ph = 0;
@@ -190,10 +194,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
                 // interior tile (all but the first / last of a block): nothing but address arithmetic and LDGSTS
                 const unsigned char *src = in + 2 * w0;
 #pragma unroll 4
-                for (int c = lane; c < nchunks; c += 32)
+                for (int c = ptid; c < nchunks; c += 32 * UM_PROD_WARPS)
                     cp_async16_s(sbase + UmLayout<P>::swz(16u * (uint32_t)c), src + 16 * c);
             } else {
-                for (int c = lane; c < nchunks; c += 32) {
+                for (int c = ptid; c < nchunks; c += 32 * UM_PROD_WARPS) {
                     const long long s0 = w0 + 8LL * c;
                     const uint32_t off = UmLayout<P>::swz(16u * (uint32_t)c);
                     if (s0 >= 0 && s0 + 8 <= f.n_in) {
@@ -220,10 +224,10 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
             }
             if (slow) fence_proxy_async();
             cp_async_arrive_noinc(full_bar(stage));
-            if (++stage == UM_STAGES) { stage = 0; ph ^= 1u; }
+            if (++stage == NST) { stage = 0; ph ^= 1u; }
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp == 1) {
+    } else if (warp == UM_MMA_WARP) {
         // ================= MMA issuer =================
         const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         const uint64_t bdesc0 = smem_desc(tab_s, 128, 256, 0);
@@ -246,15 +250,21 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
                 umma_commit(accf_bar(as));      // ... and the accumulator set is complete
             }
             __syncwarp();
-            if (++stage == UM_STAGES) { stage = 0; ph ^= 1u; }
+            if (++stage == NST) { stage = 0; ph ^= 1u; }
             as ^= 1;
             if (as == 0) aph ^= 1u;
         }
     } else {
-        // ================= epilogue: warpgroup g owns accumulator set g =================
-        const int ew = warp - 2, g = ew >> 2;
+        // ================= epilogue: 4 warpgroups; warpgroup wg works on accumulator set wg & 1 and converts the
+        // pieces 2h, 2h+1 (h = wg >> 1) of every tile of that set.  A piece = 8 candidates (16 columns of each digit) of
+        // one 128-row block; a tile has 4 (MB * PC/8).  Both halves of a set run concurrently: twice the warps hide the
+        // TMEM / shared / conversion latencies, and the set returns to the MMA warp in half the time. =================
+        const int ew = warp - UM_EPI_WARP0, wg = ew >> 2, g = wg & 1, h = wg >> 1;
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-        uint8_t *stg = gen + (size_t)UM_STAGES * SB + (size_t)KS * N * 32 + (size_t)ew * 32 * P * 8;
+        constexpr int PPB = PC / 8;                  // pieces per 128-row block
+        constexpr int SW = (P >= 16 ? 16 : 8) / 2;   // 16-byte chunks per staged row: the warp's share of an output row
+        constexpr int STG_BYTES = DEC ? 6144 : 32 * SW * 16;
+        uint8_t *stg = gen + (size_t)NST * SB + (size_t)KS * N * 32 + (size_t)ew * STG_BYTES;
         const float sc0 = a.sc[0], sc2 = a.sc[2];
         const int c10[2] = {a.magic[0][0], a.magic[1][0]}, m2[2] = {a.magic[0][2], a.magic[1][2]};
         uint32_t aph = 0;
@@ -263,91 +273,116 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
             if ((it & 1) != g) continue;
             const int ch = (int)(w / a.ntiles);
             const long long row0 = (w % a.ntiles) * (long long)TILE_ROWS;  // first window row of the tile
-            const long long m0 = row0 * P;                                    // D == 1: its first output
             float2 *out = (float2 *)f.out + (long long)ch * f.out_stride;
             mbar_wait(accf_bar(g), aph);
+            aph ^= 1u;
             tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * UM_ACC_COLS);
-            // 4 pieces per tile (MB * P/8 == 4): piece = 8 phases of one 128-row block = 16 columns of each digit.
-            // The TMEM loads of piece i+1 are in flight while piece i is converted and staged.
-            constexpr int PPB = PC / 8;  // pieces per 128-row block
-            uint32_t v[2][3][16];
-            long long mk = 0;  // DEC: next kept output of this lane's row
-            int nv = -1;       // DEC: its offset inside the row
-            auto issue = [&](int pi, uint32_t (&d)[3][16]) {
-                const uint32_t col = tbase + (uint32_t)((pi / PPB) * N + 16 * (pi % PPB));
-                tmem_ld16(col, d[0]);
-                tmem_ld16(col + 2 * PC, d[1]);
-                tmem_ld16(col + 4 * PC, d[2]);
-            };
-            issue(0, v[0]);
+            long long pos0 = 0, m_lo = 0;  // DEC: sample offset of the warp's 32-row span, first kept output inside it
+            int n_m = 0;                   // DEC: kept outputs inside it
 #pragma unroll
-            for (int pi = 0; pi < 4; ++pi) {
-                const int mb = pi / PPB, pc = pi % PPB;
-                tmem_ld_wait();
-                if (pi + 1 < 4) issue(pi + 1, v[(pi + 1) & 1]);
-                uint32_t (&d)[3][16] = v[pi & 1];
-                auto value = [&](int i) -> float {
-                    // digits 0 and 1 combine exactly in s32 ((A1 << 8) + A0, |.| < 2^31 for K <= 511; wrap-around safe);
-                    // digit 2 (|A2| < 2^23) converts with the 1.5 * 2^23 magic add: one I2F per value, not three
-                    const float f10 = (float)((int)(d[1][i] << 8) + (int)d[0][i] + c10[i & 1]);
-                    const float f2 = __int_as_float((int)d[2][i] + m2[i & 1]) - 12582912.0f;
-                    return fmaf(f2, sc2, f10 * sc0);
-                };
-                if (pi == 3) {
-                    // every accumulator of this set is in registers: hand the set back to the MMA warp
+            for (int pj = 0; pj < 2; ++pj) {
+                const int pi = 2 * h + pj, mb = pi / PPB, pc = pi % PPB;
+                uint32_t d[3][16];
+                {
+                    const uint32_t col = tbase + (uint32_t)(mb * N + 16 * pc);
+                    tmem_ld16(col, d[0]);
+                    tmem_ld16(col + 2 * PC, d[1]);
+                    tmem_ld16(col + 4 * PC, d[2]);
+                    tmem_ld_wait();
+                }
+                if (pj == 1) {
+                    // this warp's share of the set is in registers: hand it back to the MMA warp (8 warps arrive)
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acce_bar(g));
                 }
                 if constexpr (DEC) {
-                    // candidates 8pc .. 8pc+7 of window row `row`: offset g*u inside the row is a kept output iff it
-                    // equals the running next kept position (row-relative); at most one division per row
-                    constexpr int G = R / PC;
-                    const long long row = row0 + mb * 128 + quad * 32 + lane;
-                    if (pc == 0) {
-                        mk = (row * R + f.D - 1) / f.D;            // first kept output at or after the row start
-                        nv = (int)(mk * f.D - row * R);            // its offset inside the row (may be >= R: none)
-                    }
+                    // Only ~R/D of a row's candidates are kept outputs, at lane-dependent places.  The piece's raw
+                    // accumulators (8 candidates x 3 digits x (I, Q) = 48 words = 12 chunks per row) go to the warp's
+                    // staging tile (chunk (c + row) mod 12: conflict-free), then the lanes walk the kept outputs of
+                    // the warp's 32-row span -- consecutive m, so conversion work and stores are dense.
+                    constexpr int G = R / PC, LG = (G == 1) ? 0 : (G == 2) ? 1 : 2;
+                    uint4 *srow = reinterpret_cast<uint4 *>(stg) + lane * 12;
 #pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        if (G * (8 * pc + u) == nv) {
-                            if (mk < f.n_out) out[mk] = make_float2(value(2 * u), value(2 * u + 1));
-                            ++mk;
-                            nv += f.D;
+                    for (int dg = 0; dg < 3; ++dg)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            int c = dg * 4 + q + (lane % 12);
+                            if (c >= 12) c -= 12;
+                            srow[c] = make_uint4(d[dg][4 * q], d[dg][4 * q + 1], d[dg][4 * q + 2], d[dg][4 * q + 3]);
+                        }
+                    __syncwarp();
+                    if (pj == 0 || PPB == 1) {
+                        pos0 = (row0 + mb * 128 + quad * 32) * (long long)R;  // first sample offset of the warp's span
+                        m_lo = (pos0 + f.D - 1) / f.D;                        // first kept output inside it
+                        n_m = (int)((pos0 + 32 * R + f.D - 1) / f.D - m_lo);  // kept outputs inside it
+                    }
+                    for (int i = lane; i < n_m; i += 32) {
+                        const long long m = m_lo + i;
+                        const int pos = (int)(m * f.D - pos0);
+                        const int r = pos / R, u = (pos % R) >> LG;
+                        if ((u >> 3) == pc && m < f.n_out) {
+                            const int uu = u & 7, cb = uu >> 1, rot = r % 12;
+                            const unsigned char *rowp = stg + r * 192 + (uu & 1) * 8;
+                            int c0 = cb + rot, c1 = 4 + cb + rot, c2 = 8 + cb + rot;
+                            if (c0 >= 12) c0 -= 12;
+                            if (c1 >= 12) c1 -= 12;
+                            if (c2 >= 12) c2 -= 12;
+                            const uint2 a0 = *reinterpret_cast<const uint2 *>(rowp + c0 * 16);
+                            const uint2 a1 = *reinterpret_cast<const uint2 *>(rowp + c1 * 16);
+                            const uint2 a2 = *reinterpret_cast<const uint2 *>(rowp + c2 * 16);
+                            const float fI = (float)((int)(a1.x << 8) + (int)a0.x + c10[0]);
+                            const float fQ = (float)((int)(a1.y << 8) + (int)a0.y + c10[1]);
+                            const float gI = __int_as_float((int)a2.x + m2[0]) - 12582912.0f;
+                            const float gQ = __int_as_float((int)a2.y + m2[1]) - 12582912.0f;
+                            out[m] = make_float2(fmaf(gI, sc2, fI * sc0), fmaf(gQ, sc2, fQ * sc0));
                         }
                     }
+                    __syncwarp();
                 } else {
                     float y[16];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) y[i] = value(i);
-                    // row `lane` of the warp's staging tile, chunks 4pc .. 4pc+3, XOR-swizzled: conflict-free both ways
+                    for (int i = 0; i < 16; ++i) {
+                        // digits 0 and 1 combine exactly in s32 ((A1 << 8) + A0, |.| < 2^31 for K <= 511; wrap-around
+                        // safe); digit 2 (|A2| < 2^23) converts with the 1.5 * 2^23 magic add: one I2F per value
+                        const float f10 = (float)((int)(d[1][i] << 8) + (int)d[0][i] + c10[i & 1]);
+                        const float f2 = __int_as_float((int)d[2][i] + m2[i & 1]) - 12582912.0f;
+                        y[i] = fmaf(f2, sc2, f10 * sc0);
+                    }
+                    // row `lane` of the warp's staging tile (SW chunks per row), XOR-swizzled: conflict-free both ways
+                    const int cl0 = 4 * (pc % (SW / 4));
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
-                        const int c = 4 * pc + q;
-                        const int pcn = (P == 8) ? (c ^ ((lane >> 1) & 3)) : (c ^ (lane & 7));
-                        *reinterpret_cast<float4 *>(stg + ((size_t)lane * CPR + pcn) * 16) =
+                        const int c = cl0 + q;
+                        const int pcn = (SW == 4) ? (c ^ ((lane >> 1) & 3)) : (c ^ (lane & 7));
+                        *reinterpret_cast<float4 *>(stg + ((size_t)lane * SW + pcn) * 16) =
                             make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
                     }
-                    if (pc == PPB - 1) {
+                    if (cl0 + 4 == SW) {
                         __syncwarp();
-                        // the warp's 32 rows are 32*P consecutive outputs: 512 contiguous bytes per store instruction
-                        const long long mrow = m0 + (long long)(mb * 128 + quad * 32) * P;
-                        float4 val[CPR];
+                        // the warp's 32 (sub-)rows: row r holds outputs (row index)*P + phase0 .. + 2 SW - 1
+                        const int phase0 = (P == 32) ? 16 * h : 0;
+                        const long long mrow = (row0 + mb * 128 + quad * 32) * (long long)P;
+                        float4 val[SW];
 #pragma unroll
-                        for (int i = 0; i < CPR; ++i) {
+                        for (int i = 0; i < SW; ++i) {
                             const int q = i * 32 + lane;
-                            const int row = q / CPR, c = q % CPR;
-                            const int pcn = (P == 8) ? (c ^ ((row >> 1) & 3)) : (c ^ (row & 7));
-                            val[i] = *reinterpret_cast<const float4 *>(stg + ((size_t)row * CPR + pcn) * 16);
+                            const int row = q / SW, c = q % SW;
+                            const int pcn = (SW == 4) ? (c ^ ((row >> 1) & 3)) : (c ^ (row & 7));
+                            val[i] = *reinterpret_cast<const float4 *>(stg + ((size_t)row * SW + pcn) * 16);
                         }
                         if (mrow + 32 * P <= f.n_out) {
 #pragma unroll
-                            for (int i = 0; i < CPR; ++i) *reinterpret_cast<float4 *>(out + mrow + 2 * (i * 32 + lane)) = val[i];
+                            for (int i = 0; i < SW; ++i) {
+                                const int q = i * 32 + lane;
+                                *reinterpret_cast<float4 *>(out + mrow + (q / SW) * P + phase0 + 2 * (q % SW)) = val[i];
+                            }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < CPR; ++i) {
-                                const long long m = mrow + 2LL * (i * 32 + lane);
+                            for (int i = 0; i < SW; ++i) {
+                                const int q = i * 32 + lane;
+                                const long long m = mrow + (long long)(q / SW) * P + phase0 + 2 * (q % SW);
                                 if (m + 1 < f.n_out) *reinterpret_cast<float4 *>(out + m) = val[i];
                                 else if (m < f.n_out) out[m] = make_float2(val[i].x, val[i].y);
                             }
@@ -356,12 +391,11 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
                     }
                 }
             }
-            aph ^= 1u;
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) {
+    if (warp == UM_MMA_WARP) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
     }
@@ -396,7 +430,7 @@ bool fir_umma_geometry(int K, int D, int *R_out, int *PC_out) {
         const int forced = e ? std::atoi(e) : 0;
         for (int p : {8, 16, 32}) {
             const int ks = fir_umma_ksteps(K, p, p);
-            if (um_smem_bytes(p, p, ks, false) > 220 * 1024) continue;
+            if (um_smem_bytes(p, p, ks, false, 2) > 220 * 1024) continue;
             // cycles per output ~ KS * max(45, N/2) / (128 P): wide rows amortise the band padding
             const double c = (forced == p) ? 0.0 : ks * std::max(45.0, 3.0 * p) / (128.0 * p);
             if (c < best_c) { best_c = c; best = p; }
@@ -408,7 +442,7 @@ bool fir_umma_geometry(int K, int D, int *R_out, int *PC_out) {
     const int g = gcd_i(D, 32);
     if (g > 4) return false;  // fewer than 8 candidates per 32-sample row: N would drop below the M = 128 minimum of 16
     const int ks = fir_umma_ksteps(K, 32, 32 / g);
-    if (um_smem_bytes(32, 32 / g, ks, true) > 220 * 1024) return false;
+    if (um_smem_bytes(32, 32 / g, ks, true, 2) > 220 * 1024) return false;
     *R_out = 32;
     *PC_out = 32 / g;
     return true;
@@ -484,13 +518,18 @@ bool fir_umma_build_tables(const float *taps, int K, bool tc, int R, int PC, std
 int fir_umma_launch(const FirArgs &f, int R, int PC, const uint8_t *d_tables, const int magic[2][3], const float sc[3], cudaStream_t st) {
     if (f.n_out <= 0) return SDR_OK;
     if (f.K > UM_MAX_K || (f.D == 1 && R != PC) || (f.D != 1 && R != 32)) return SDR_ERR_UNSUPPORTED;
-    if (((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 15) || (f.out_stride & 1) || (f.in_stride & 7) || ((uintptr_t)f.hist & 1))
+    // rows of a multi-channel call must keep the 16-byte alignment of the first one (strides are ignored for one channel)
+    if (((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 15) || ((uintptr_t)f.hist & 1) ||
+        (f.n_ch > 1 && ((f.out_stride & 1) || (f.in_stride & 7))))
         return SDR_ERR_UNSUPPORTED;
     const bool dec = f.D != 1;
     const int KS = fir_umma_ksteps(f.K, R, PC);
-    const size_t smem = um_smem_bytes(R, PC, KS, dec);
+    int stages = UM_STAGES;
+    while (stages > 2 && um_smem_bytes(R, PC, KS, dec, stages) > 220 * 1024) --stages;
+    const size_t smem = um_smem_bytes(R, PC, KS, dec, stages);
     if (smem > 220 * 1024) return SDR_ERR_UNSUPPORTED;
     UmArgs a;
+    a.stages = stages;
     a.f = f;
     a.KS = KS;
     long long d = (f.first - (f.K - 1)) % 8;
