@@ -29,10 +29,11 @@ import numpy as np  # noqa: E402
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the `ncu --set full` captures
 # summarised under profiles/ (same command line as the bench, one launch).  null = not captured for that workload.
 NCU_TRAFFIC = {
-    "c2_fft1024_u8iq_2p28": (2.627e9, "profiles/r01_prof_fft_r01b.txt"),
+    "c2_fft1024_u8iq_2p28": (2.628e9, "profiles/r01_prof_fft1024_u8_v3.txt"),
     "fir64_d1_u8iq_2p26": (6.124e8, "profiles/r01_prof_fir_umma_c1_v2.txt"),
     "fir255_d1_u8iq_2p26": (6.122e8, "profiles/r01_prof_fir_umma_k255_v2.txt"),
     "c5_fft65536_c64_2p27": (2.102e9, "profiles/r01_prof_fft_l2_64k_v1.txt"),
+    "fir255_d10_u8iq_2p26": (1.624e8, "profiles/r01_prof_fir_umma_c3_v1.txt"),
 }
 
 
@@ -119,12 +120,7 @@ def wl_fft1024_u8(torch, sdr, dev, log2_samples=28):
         return float(host["out"][batches - 1, 0].real)
 
     def cpu(units, threads):
-        import oracle_lib as O
-        import gen
-        iq = gen.random_u8(2 * units, 5)
-        t0 = time.perf_counter()
-        O.fft_batch_u8(iq, n, threads)
-        return time.perf_counter() - t0
+        return _cpu_fft_u8(units, threads)
 
     return dict(name="c2_fft1024_u8iq_2p%d" % log2_samples, units=samples, bytes_per_unit=10.0, step=step,
                 e2e_setup=e2e_setup, e2e_step=e2e_step, h2d=2 * samples, d2h=8 * samples, cpu=cpu,
@@ -257,7 +253,7 @@ def make_workload(name, torch, sdr, dev):
     raise SystemExit("unknown workload " + name)
 
 
-CPU_SAMPLE_UNITS = {"c2": 1 << 26, "fir": 1 << 22, "c5": 1 << 25, "c4": 1 << 19}
+CPU_SAMPLE_UNITS = {"c2": 1 << 28, "fir": 1 << 24, "c5": 1 << 26, "c4": 1 << 19}
 
 
 def cpu_sample_units(wl):
@@ -286,8 +282,8 @@ def run_reference(args):
     # build the workload description without touching a GPU
     name = args.workload
     cpu_only = {
-        "c2": (lambda u, t: _cpu_fft_u8(u, t), 1 << 26, "c2_fft1024_u8iq_2p28"),
-        "default": (lambda u, t: _cpu_fft_u8(u, t), 1 << 26, "c2_fft1024_u8iq_2p28"),
+        "c2": (lambda u, t: _cpu_fft_u8(u, t), 1 << 28, "c2_fft1024_u8iq_2p28"),
+        "default": (lambda u, t: _cpu_fft_u8(u, t), 1 << 28, "c2_fft1024_u8iq_2p28"),
     }
     fn, units, wname = cpu_only.get(name, cpu_only["c2"])
     for _ in range(args.warmup):
@@ -300,7 +296,7 @@ def run_reference(args):
         "impl": "reference", "metric": "FIR/FFT Gsamples/s", "value": value, "unit": "Gsamples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wname, "sample_per_step": units, "note": "CPU oracle port of the reference path "
+        "config": {"workload": wname, "samples_per_step": units, "note": "CPU oracle port of the reference path "
                    "(unpack + per-call-planned radix-4 FFT + shift/norm), std::thread over independent blocks"},
         "cpu_baseline": {"value": value, "unit": "Gsamples/s", "cores": threads, "kind": "port",
                          "sample": "%d samples (%d x 1024-pt blocks) per step" % (units, units // 1024)},
@@ -310,10 +306,15 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+_CPU_INPUT = {}
+
+
 def _cpu_fft_u8(units, threads):
     import oracle_lib as O
-    import gen
-    iq = gen.random_u8(2 * units, 5)
+    if units not in _CPU_INPUT:  # generated once, outside the timed region
+        _CPU_INPUT.clear()
+        _CPU_INPUT[units] = np.random.default_rng(5).integers(0, 256, 2 * units, dtype=np.uint8)
+    iq = _CPU_INPUT[units]
     t0 = time.perf_counter()
     O.fft_batch_u8(iq, 1024, threads)
     return time.perf_counter() - t0
