@@ -172,6 +172,41 @@ def wl_fir_u8(torch, sdr, dev, K=64, D=1, log2_samples=26, complex_taps=False):
                 desc="fused u8-IQ unpack + %d-tap %s FIR, decimation %d" % (K, "complex" if complex_taps else "real", D))
 
 
+def wl_c3_chain(torch, sdr, dev, log2_samples=26, converter=0):
+    """C3 end to end on the device: u8 IQ -> 255-tap FIR, Decimate 10 (2.4 MS/s -> 240 kS/s) -> SampleRate x0.2
+    (-> 48 kS/s, converter 0 = SincBestQuality, the reference's default) with every intermediate left in HBM."""
+    import gen
+    samples = 1 << log2_samples
+    D = 10
+    taps = gen.lowpass_taps(255, 100e3, 2.4e6)
+    g = torch.Generator(device=dev).manual_seed(0x5D12B200 + 3)
+    raw = torch.randint(0, 256, (2 * samples,), dtype=torch.uint8, device=dev, generator=g)
+    n_mid = samples // D + 1
+    mid = torch.empty(n_mid, dtype=torch.complex64, device=dev)
+    n_fin = n_mid // 5 + 16
+    fin = torch.empty(n_fin, dtype=torch.complex64, device=dev)
+    st = torch.cuda.current_stream(dev)
+    fir = sdr.Fir(taps, "u8iq", decimation=D, device=dev.index, stream=st)
+    src = sdr.SampleRate(converter, 2, device=dev.index, stream=st)
+
+    def step():
+        got = fir.process_dev(raw, samples, mid, n_mid)
+        src.process_dev(0.2, mid, got, fin, n_fin)
+
+    def cpu(units, threads):
+        import oracle_lib as O
+        iq = gen.random_u8(2 * units, 5)
+        t0 = time.perf_counter()
+        O.fir_u8_mt(iq, taps, D, threads)
+        return time.perf_counter() - t0
+
+    name = {0: "sincbest", 1: "sincmedium", 2: "sincfastest", 3: "zoh", 4: "linear"}[converter]
+    return dict(name="c3_chain_fir255_d10_%s_2p%d" % (name, log2_samples), units=samples, bytes_per_unit=2.0 + 8.0 / 50,
+                step=step, e2e_setup=None, e2e_step=None, h2d=2 * samples, d2h=8 * n_fin, cpu=cpu,
+                dtype="u8 x s8 -> s32 (tcgen05), f64 sinc accumulation", kernel="fir_umma_kernel + src_sinc_kernel",
+                desc="u8 IQ -> 255-tap FIR /10 -> SampleRate x0.2 (%s), device resident" % name)
+
+
 def wl_fft_c64(torch, sdr, dev, logn=12, log2_samples=27):
     n = 1 << logn
     samples = 1 << log2_samples
@@ -238,6 +273,12 @@ def make_workload(name, torch, sdr, dev):
         return wl_fir_u8(torch, sdr, dev, 64, 1, complex_taps=True)
     if name in ("c3", "fir255_d10_u8"):
         return wl_fir_u8(torch, sdr, dev, 255, 10)
+    if name == "c3chain":
+        return wl_c3_chain(torch, sdr, dev)
+    if name == "c3chain_linear":
+        return wl_c3_chain(torch, sdr, dev, converter=4)
+    if name == "c3chain_fastest":
+        return wl_c3_chain(torch, sdr, dev, converter=2)
     if name == "fir255_u8":
         return wl_fir_u8(torch, sdr, dev, 255, 1)
     if name == "c4":

@@ -111,7 +111,7 @@ def test_channelizer_small(sdr):
 
 
 @pytest.mark.parametrize("typ", ["Linear", "ZeroOrderHold", "SincFastest", "SincMediumQuality"])
-@pytest.mark.parametrize("ratio", [0.2, 0.08, 1.0 / 3.0, 1.5, 48000.0 / 44100.0])
+@pytest.mark.parametrize("ratio", [0.2, 0.08, 1.0 / 3.0, 1.5, 2.0, 48000.0 / 44100.0])
 def test_samplerate_process_matches_oracle(sdr, typ, ratio):
     ct = getattr(sdr.ConverterType, typ)
     x = gen.complex_noise(9000, 12).view(np.float32).reshape(-1, 2)
@@ -135,6 +135,42 @@ def test_samplerate_process_matches_oracle(sdr, typ, ratio):
         # f64 accumulation in identical order: equal up to the final f32 rounding
         assert np.abs(ya - yb).max() <= 1.2e-7 * max(1.0, np.abs(yb).max())
         assert (ya.view(np.uint32) != yb.view(np.uint32)).mean() < 1e-3
+
+
+def test_sinc_polyphase_path_equals_per_tap_kernel_bit_for_bit(sdr):
+    """Dyadic steps (ratio 0.2, 0.08, 0.5, 2.0) take the polyphase kernel: per-phase coefficient tables + the same f64
+    multiply-add chain.  A second process with SDR_SRC_NO_POLY set runs the per-tap kernel: identical bits, identical
+    counts, for every converter including SincBestQuality (the reference's default, signal/mod.rs:83)."""
+    import subprocess
+    import sys
+    import tempfile
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import gen, sdr_b200 as sdr
+x = gen.complex_noise(30000, 12).view(np.float32).reshape(-1, 2)
+outs = []
+for typ in (0, 1, 2):
+    for ratio in (0.2, 0.08, 0.5, 2.0):
+        for ch in (1, 2):
+            a = sdr.SampleRate(typ, ch)
+            xx = x if ch == 2 else x[:, :1]
+            pos = 0
+            for blk in (5, 12000, 4096, 9000, 0, 0):
+                u, o = a.process(ratio, xx[pos:pos + blk], 8192)
+                pos += u
+                outs.append(np.array([u, len(o)], np.float32))
+                outs.append(o.ravel())
+np.save(sys.argv[1], np.concatenate(outs))
+""" % (os.path.join(os.path.dirname(__file__), "..", "unnamed-rust-sdr_b200"), os.path.dirname(__file__))
+    res = []
+    for env_extra in ({}, {"SDR_SRC_NO_POLY": "1"}):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            env = dict(os.environ, **env_extra)
+            subprocess.check_call([sys.executable, "-c", code, f.name], env=env)
+            res.append(np.load(f.name))
+    assert res[0].shape == res[1].shape and res[0].size > 100000
+    assert np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32))
 
 
 def test_samplerate_contract(sdr):

@@ -963,6 +963,7 @@ struct sdr_src {
     int cur = 0;
     DevBuf carry;  // ZOH / linear: the frame before in[0]
     DevBuf d_out;
+    DevBuf coef;   // sinc: per-phase wing coefficients of the polyphase fast path
 };
 
 static bool bad_ratio(double r) { return !(r >= 1.0 / 256.0 && r <= 256.0); }
@@ -976,7 +977,7 @@ static void src_free(sdr_src *s) {
     if (!s) return;
     DeviceGuard g(s->dev);
     if (s->d_table) cudaFree(s->d_table);
-    s->v[0].release(); s->v[1].release(); s->carry.release(); s->d_out.release();
+    s->v[0].release(); s->v[1].release(); s->carry.release(); s->d_out.release(); s->coef.release();
     s->stream.release();
     delete s;
 }
@@ -1191,6 +1192,8 @@ static int src_process_impl(sdr_src *s, SDR_SRC_DATA *d, bool dev_ptrs) {
         dout = (float *)s->d_out.p;
     }
     L.out = dout;
+    if ((size_t)(wc + 2) * 32 * sizeof(double) <= ((size_t)32 << 20) && s->coef.reserve((size_t)(wc + 2) * 32 * sizeof(double)) == SDR_OK)
+        L.coef = (double *)s->coef.p;
     rc = src_launch(L, st);
     if (rc) return rc;
     if (!dev_ptrs && m > 0) SDR_CUDA_TRY(cudaMemcpyAsync(d->data_out, dout, (size_t)m * fb, cudaMemcpyDeviceToHost, st));

@@ -105,6 +105,9 @@ struct SrcLaunch {
     long long half_len;
     double rq, rho;
     long long wc;
+    // polyphase fast path (filled by src_launch when the positions are exact): device scratch for the per-phase wing
+    // coefficients, 2 * 16 * (wc + 2) doubles, or null to force the per-tap kernel
+    double *coef = nullptr;
 };
 int src_launch(const SrcLaunch &s, cudaStream_t st);
 // the windowed-sinc half table of converter `type` (0..2), computed once on the host in f64

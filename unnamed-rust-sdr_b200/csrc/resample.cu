@@ -7,6 +7,7 @@
 // All position and coefficient arithmetic is f64 with explicit _rn intrinsics (no FMA
 // contraction), so a GPU output equals the CPU restatement's bit for bit.
 #include <cmath>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -68,6 +69,92 @@ __global__ void src_sinc_kernel(SrcLaunch s) {
         right = __dadd_rn(right, __dmul_rn(co, (double)s.v[(j + s.origin) * s.channels + c]));
     }
     s.out[gid] = (float)__dmul_rn(s.rho, __dadd_rn(left, right));
+}
+
+// ---- polyphase fast path ---------------------------------------------------------------------------------------
+// When step = 1/ratio is k/q with q in {1,2,4,8,16} and the start position lies on a 2^-16 grid, every position
+// pos + m*step and every distance T - j is EXACT in f64, so the coefficient of tap distance d depends only on
+// (m mod q, d): q tables of wc + 2 entries per wing, computed once per call with the very operations of
+// src_sinc_kernel (bit-identical coefficients), and the per-output work is reduced to the f64 multiply-add chain in
+// the specified order (left wing far -> near, right wing far -> near).  The reference's ratios (0.2, 0.08, 1/3 is not
+// dyadic and stays on the per-tap kernel) hit it.  A CTA stages its window of input frames in shared memory as f64.
+struct PolyArgs {
+    SrcLaunch s;
+    int q;
+    double frac[16];   // T - floor(T) for outputs m = 0..q-1
+    int dmaxL[16], dmaxR[16];  // largest tap distance inside the table (k < half_len), per phase
+};
+
+__global__ void src_sinc_coef_kernel(PolyArgs a) {
+    const long long W = a.s.wc + 2;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= 2LL * a.q * W) return;
+    const int wing = (int)(gid / (a.q * W));
+    const int p = (int)((gid / W) % a.q);
+    const long long d = gid % W;
+    // left: T - j = d + frac ; right: j - T = d - frac   (both exact)
+    const double dist = wing == 0 ? __dadd_rn((double)d, a.frac[p]) : __dsub_rn((double)d, a.frac[p]);
+    double co = 0.0;
+    if (dist >= 0.0) {
+        const double fi = __dmul_rn(dist, a.s.rq);
+        const long long k = (long long)fi;
+        if (k < a.s.half_len) {
+            const double fr = __dsub_rn(fi, (double)k);
+            const double t0 = (double)__ldg(a.s.table + k), t1 = (double)__ldg(a.s.table + k + 1);
+            co = __dadd_rn(t0, __dmul_rn(fr, __dsub_rn(t1, t0)));
+        }
+    }
+    a.s.coef[gid] = co;
+}
+
+template <int CH>
+__global__ void __launch_bounds__(128) src_sinc_poly_kernel(PolyArgs a) {
+    extern __shared__ double xs[];
+    const SrcLaunch &s = a.s;
+    const int tid = threadIdx.x;
+    const long long W = s.wc + 2;
+    const long long mb0 = (long long)blockIdx.x * 128;
+    const long long mb1 = min(mb0 + 127, s.n_out - 1);
+    const long long i_first = (long long)floor(out_position(s.pos, mb0, s.step));
+    const long long i_last = (long long)floor(out_position(s.pos, mb1, s.step));
+    long long jlo = i_first - s.wc - 1, jhi = i_last + s.wc + 1;
+    if (jlo < 0) jlo = 0;
+    if (jhi > s.have - 1) jhi = s.have - 1;
+    const long long nfr = jhi - jlo + 1;
+    for (long long i = tid; i < nfr * CH; i += 128) xs[i] = (double)s.v[jlo * CH + i];
+    __syncthreads();
+    const long long m = mb0 + tid;
+    if (m >= s.n_out) return;
+    const double T = out_position(s.pos, m, s.step);
+    const long long i0 = (long long)floor(T);
+    const int p = (int)(m % a.q);
+    double left[CH], right[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) { left[c] = 0.0; right[c] = 0.0; }
+    {   // left wing, far -> near: j = i0 - d, d from dmax down to 0, inside [0, have)
+        long long dhi = min((long long)a.dmaxL[p], min(s.wc + 1, i0));
+        long long dlo = max(0LL, i0 - (s.have - 1));
+        const double *co = s.coef + (0 * a.q + p) * W;
+        for (long long d = dhi; d >= dlo; --d) {
+            const double c0 = __ldg(co + d);
+            const double *x = xs + (i0 - d - jlo) * CH;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) left[c] = __dadd_rn(left[c], __dmul_rn(c0, x[c]));
+        }
+    }
+    {   // right wing, far -> near: j = i0 + d, d from dmax down to 1
+        long long dhi = min((long long)a.dmaxR[p], min(s.wc + 1, s.have - 1 - i0));
+        long long dlo = max(1LL, -i0);
+        const double *co = s.coef + (1 * a.q + p) * W;
+        for (long long d = dhi; d >= dlo; --d) {
+            const double c0 = __ldg(co + d);
+            const double *x = xs + (i0 + d - jlo) * CH;
+#pragma unroll
+            for (int c = 0; c < CH; ++c) right[c] = __dadd_rn(right[c], __dmul_rn(c0, x[c]));
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) s.out[m * CH + c] = (float)__dmul_rn(s.rho, __dadd_rn(left[c], right[c]));
 }
 
 // ---- coefficient design (host, f64, done once per converter type) ---------------------------
@@ -132,14 +219,66 @@ double src_sinc_wing(int type, double ratio, double *rq, double *rho, long long 
     return wing;
 }
 
+// the polyphase path applies when every position of the call is exact in f64 (see above); fills PolyArgs
+static bool poly_plan(const SrcLaunch &s, PolyArgs &a) {
+    static const bool disabled = std::getenv("SDR_SRC_NO_POLY") != nullptr;  // A/B switch for the parity test
+    if (disabled || !s.coef || s.channels > 2 || s.origin != 0 || s.wc + 2 > (1 << 20)) return false;
+    int q = 0;
+    for (int c : {1, 2, 4, 8, 16}) {
+        const double v = s.step * c;
+        if (v == std::floor(v) && v < 1e9) { q = c; break; }
+    }
+    if (!q) return false;
+    const double g = s.pos * 65536.0;
+    if (g != std::floor(g) || std::fabs(s.pos) > 1e9 || (double)s.n_out * s.step > 1e9) return false;
+    a.s = s;
+    a.q = q;
+    for (int p = 0; p < q; ++p) {
+        const double T = s.pos + (double)p * s.step;  // exact
+        a.frac[p] = T - std::floor(T);
+        // largest distance whose table index stays inside: same f64 products as the kernel
+        int dl = -1, dr = -1;
+        for (long long d = 0; d <= s.wc + 1; ++d) {
+            const double fl = ((double)d + a.frac[p]) * s.rq;
+            if ((long long)fl < s.half_len) dl = (int)d; else break;
+        }
+        for (long long d = 1; d <= s.wc + 1; ++d) {
+            const double fr = ((double)d - a.frac[p]) * s.rq;
+            if ((long long)fr < s.half_len) dr = (int)d; else break;
+        }
+        a.dmaxL[p] = dl;
+        a.dmaxR[p] = dr;
+    }
+    for (int p = q; p < 16; ++p) { a.frac[p] = 0.0; a.dmaxL[p] = -1; a.dmaxR[p] = -1; }
+    return true;
+}
+
 int src_launch(const SrcLaunch &s, cudaStream_t st) {
     const long long total = s.n_out * s.channels;
     if (total <= 0) return SDR_OK;
     const unsigned grid = (unsigned)((total + 127) / 128);
-    if (s.type == SDR_SRC_ZERO_ORDER_HOLD || s.type == SDR_SRC_LINEAR)
+    if (s.type == SDR_SRC_ZERO_ORDER_HOLD || s.type == SDR_SRC_LINEAR) {
         src_zoh_linear_kernel<<<grid, 128, 0, st>>>(s);
-    else
-        src_sinc_kernel<<<grid, 128, 0, st>>>(s);
+        count_launch();
+        return launch_status();
+    }
+    PolyArgs a;
+    if (poly_plan(s, a)) {
+        const size_t frames = (size_t)(127.0 * s.step) + 2 * (size_t)s.wc + 8;
+        const size_t smem = frames * s.channels * sizeof(double);
+        if (smem <= 200 * 1024) {
+            const long long ncoef = 2LL * a.q * (s.wc + 2);
+            src_sinc_coef_kernel<<<(unsigned)((ncoef + 255) / 256), 256, 0, st>>>(a);
+            count_launch();
+            auto kern = s.channels == 1 ? src_sinc_poly_kernel<1> : src_sinc_poly_kernel<2>;
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return cuda_status(e);
+            kern<<<(unsigned)((s.n_out + 127) / 128), 128, smem, st>>>(a);
+            count_launch();
+            return launch_status();
+        }
+    }
+    src_sinc_kernel<<<grid, 128, 0, st>>>(s);
     count_launch();
     return launch_status();
 }

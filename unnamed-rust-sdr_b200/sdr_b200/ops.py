@@ -409,6 +409,16 @@ class SampleRate:
             raise ResampleError(rc)
         return d.input_frames_used, out[:d.output_frames_gen].copy()
 
+    def process_dev(self, ratio, d_in, n_frames, d_out, out_capacity, end_of_input=False):
+        """device-resident SampleRate::process: d_in / d_out are device buffers of interleaved f32 frames; the counts
+        come back synchronously, the samples land asynchronously on the handle's stream.  Returns (used, generated)."""
+        d = F.SrcData(_ptr(d_in) if n_frames else None, _ptr(d_out), int(n_frames), int(out_capacity), 0, 0,
+                      1 if (end_of_input or n_frames == 0) else 0, ratio)
+        rc = lib().sdr_src_process_dev(self.h, C.byref(d))
+        if rc != 0:
+            raise ResampleError(rc)
+        return d.input_frames_used, d.output_frames_gen
+
     def reset(self):
         rc = lib().sdr_src_reset(self.h)
         if rc:
