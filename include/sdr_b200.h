@@ -81,6 +81,7 @@ int sdr_unpack_u8iq_dev(const uint8_t *iq, size_t n_samples, float *out_c64, int
 #define SDR_FIR_STRICT_ORDER 1u /* f32 mul then add, k ascending, no FMA: bit-identical to Fir::apply */
 #define SDR_FIR_NO_TENSOR 2u    /* never take a tensor-core path */
 #define SDR_FIR_NO_TCGEN05 4u   /* never take the tcgen05/TMEM path (the mma.sync Toeplitz path may still run) */
+#define SDR_FIR_PLANAR 8u       /* real taps: tcgen05 kernel on de-interleaved I / Q byte planes (same bits; see fir_umma.cu) */
 
 typedef struct {
     const float *taps;   /* n_taps f32, or n_taps (re,im) pairs when taps_complex */

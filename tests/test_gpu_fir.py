@@ -213,6 +213,32 @@ def test_tcgen05_path_every_row_width(sdr, monkeypatch, P, K, tc):
     assert np.array_equal(parts.view(np.uint32), got.view(np.uint32))
 
 
+def test_planar_and_interleaved_tcgen05_kernels_agree_bit_for_bit(sdr):
+    """Real taps can run on de-interleaved byte planes (SDR_FIR_PLANAR: half the tensor work) instead of the interleaved
+    bytes.  Both accumulate exact integers and share the epilogue, so the bits must be identical -- D = 1 and
+    decimating, ragged blocks, multi-channel, 255 taps included."""
+    PLANAR = 8
+    for K in (17, 64, 150, 255):
+        taps = (np.random.default_rng(K).standard_normal(K) / np.sqrt(K)).astype(np.float32)
+        for D in (1, 2, 3, 4, 10, 12):
+            if K == 255 and D == 3:
+                continue  # the interleaved kernel has no room for 32 candidates x 255 taps
+            n = 3 * 8192 + 11
+            iq = gen.random_u8(2 * n, K + D)
+            cuts = [0, 7, 8192, 2 * 8192 + 5, n]
+            got = []
+            for flags in (0, PLANAR):
+                f = sdr.Fir(taps, "u8iq", decimation=D, flags=flags)
+                got.append(np.concatenate([f.process(iq[2 * a:2 * b]) for a, b in zip(cuts[:-1], cuts[1:])]))
+                assert f.last_path == 4
+            assert len(got[0]) == n // D
+            assert np.array_equal(got[0].view(np.uint32), got[1].view(np.uint32)), (K, D)
+        raw = gen.random_u8(2 * 3 * 9000, K).reshape(3, -1)
+        a = sdr.Fir(taps, "u8iq", n_channels=3).process(raw)
+        b = sdr.Fir(taps, "u8iq", n_channels=3, flags=PLANAR).process(raw)
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
 def test_tensor_path_multichannel_and_impulse(sdr):
     taps = gen.lowpass_taps(64, 200e3, 2.048e6)
     raw = gen.random_u8(2 * 5 * 4096, 9).reshape(5, -1)

@@ -191,7 +191,7 @@ struct sdr_fir {
     uint2 *d_tc_tables = nullptr;  // tensor-core Toeplitz tap fragments (u8 input, non-strict)
     float tc_scale = 1.0f;
     uint8_t *d_um_tables = nullptr;  // tcgen05 Toeplitz digit tables (u8 input, non-strict, D == 1)
-    int um_R = 0, um_PC = 0, um_magic[2][3] = {{0, 0, 0}, {0, 0, 0}};
+    int um_R = 0, um_PC = 0, um_planar = 0, um_magic[2][3] = {{0, 0, 0}, {0, 0, 0}};
     float um_sc[3] = {0.0f, 0.0f, 0.0f};
     void *d_hist[2] = {nullptr, nullptr};
     int cur = 0;
@@ -235,13 +235,14 @@ static int fir_alloc(sdr_fir *f, void *user_stream) {
         SDR_CUDA_TRY(cudaMemcpyAsync(f->d_tc_tables, tab.data(), tab.size() * sizeof(uint2), cudaMemcpyHostToDevice, f->stream.s));
         SDR_CUDA_TRY(cudaStreamSynchronize(f->stream.s));
     }
-    int R = 0, PC = 0;
+    int R = 0, PC = 0, planar = 0;
     if (f->fmt == SDR_FMT_U8IQ && !(f->flags & (SDR_FIR_STRICT_ORDER | SDR_FIR_NO_TENSOR | SDR_FIR_NO_TCGEN05)) && f->D <= (1u << 20) &&
-        fir_umma_geometry((int)f->K, (int)f->D, &R, &PC)) {
+        fir_umma_geometry((int)f->K, (int)f->D, f->taps_complex != 0, (f->flags & SDR_FIR_PLANAR) != 0, &R, &PC, &planar)) {
         std::vector<uint8_t> tab;
-        if (fir_umma_build_tables(f->taps.data(), (int)f->K, f->taps_complex != 0, R, PC, tab, f->um_magic, f->um_sc)) {
+        if (fir_umma_build_tables(f->taps.data(), (int)f->K, f->taps_complex != 0, R, PC, planar != 0, tab, f->um_magic, f->um_sc)) {
             f->um_R = R;
             f->um_PC = PC;
+            f->um_planar = planar;
             SDR_CUDA_TRY(cudaMalloc(&f->d_um_tables, tab.size()));
             SDR_CUDA_TRY(cudaMemcpyAsync(f->d_um_tables, tab.data(), tab.size(), cudaMemcpyHostToDevice, f->stream.s));
             SDR_CUDA_TRY(cudaStreamSynchronize(f->stream.s));
@@ -338,7 +339,7 @@ static int fir_run_dev(sdr_fir *f, const void *in, size_t n_in, size_t in_stride
     const bool strict = (f->flags & SDR_FIR_STRICT_ORDER) != 0;
     int rc = SDR_ERR_UNSUPPORTED;
     if (f->d_um_tables) {
-        rc = fir_umma_launch(a, f->um_R, f->um_PC, f->d_um_tables, f->um_magic, f->um_sc, f->stream.s);
+        rc = fir_umma_launch(a, f->um_R, f->um_PC, f->um_planar != 0, f->d_um_tables, f->um_magic, f->um_sc, f->stream.s);
         if (rc == SDR_OK) f->last_path = 4;
     }
     if (rc == SDR_ERR_UNSUPPORTED && f->d_tc_tables) {

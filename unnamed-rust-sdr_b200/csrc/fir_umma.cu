@@ -401,6 +401,334 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
     }
 }
 
+// =====================================================================================================================
+// Planar variant for REAL taps (opt-in: SDR_FIR_PLANAR).  With interleaved I,Q bytes half of every real-tap B column
+// is zero (an I output never touches a Q byte): half of the tensor work and of the tap-table operand traffic is wasted.
+// Here the producers split each 16-byte chunk into its 8 I and 8 Q bytes (two PRMT pairs) and keep two byte planes per
+// stage; a k-step is 32 SAMPLES of one plane, both planes multiply the same B block (N = 3 PC) into their own
+// accumulator columns.  Rows are R BYTES apart inside a plane (16 / 32 / 64: no swizzle / SWIZZLE_32B / SWIZZLE_64B),
+// so a row spans twice the samples of the interleaved kernel: for 255 taps the MMA count per sample halves and the
+// tables shrink 4x.  Everything downstream of the MMAs (hand-over, conversion, staging, stores) is the interleaved
+// kernel's, and the results are bit-identical (test_planar_and_interleaved_...).
+// MEASURED (round 1): not faster.  ncu (profiles/r01_prof_fir_planar_k255.txt): tensor pipe 32 %, epilogue warps 62 %
+// waiting for accumulators, producers stalled on LDS -> PRMT.  The limit of this kernel family at 255 taps is the
+// 128 B/cycle shared-memory port that MMA operand fetch (140-190 KB per 4096-sample tile), the epilogue staging (64 KB)
+// and the producers share; the raw-ring -> plane conversion adds 17 KB per tile to it and puts an LDS on the
+// producers' critical path.  C1 392 vs 490, C3 483 vs 588, 255 taps D=1 343 vs 321-377 Gsamples/s: it stays opt-in.
+// =====================================================================================================================
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr) : "memory");
+}
+template <int PITCH> struct PitchLayout;  // row pitch in bytes
+template <> struct PitchLayout<16> { static constexpr uint32_t type = 0; __device__ static uint32_t swz(uint32_t o) { return o; } };
+template <> struct PitchLayout<32> { static constexpr uint32_t type = 6; __device__ static uint32_t swz(uint32_t o) { return o ^ (((o >> 7) & 1u) << 4); } };
+template <> struct PitchLayout<64> { static constexpr uint32_t type = 4; __device__ static uint32_t swz(uint32_t o) { return o ^ (((o >> 7) & 3u) << 4); } };
+
+// one plane of a stage: the 128*MB window starts R bytes apart + the KS*32-byte halo, 1024-aligned
+__host__ __device__ constexpr int um_plane_bytes(int R, int PC, int KS) {
+    return (R * (128 * (32 / PC) - 1) + 32 * KS + 1023) / 1024 * 1024;
+}
+// raw ring slot: the tile's interleaved bytes as they arrive from HBM (cp.async), before the split into planes
+__host__ __device__ constexpr int um_raw_bytes(int R, int PC, int KS) {
+    return (R * (128 * (32 / PC) - 1) + 32 * KS + 7) / 8 * 16;
+}
+constexpr int UM_RAW_SLOTS = 3;
+__host__ __device__ constexpr size_t um_planar_smem_bytes(int R, int PC, int KS, bool dec, int stages) {
+    return (size_t)KS * 3 * PC * 32 + (size_t)stages * 2 * um_plane_bytes(R, PC, KS) +
+           (dec ? (size_t)16 * 6144 : (size_t)16 * 32 * 8 * 16) + (size_t)UM_RAW_SLOTS * um_raw_bytes(R, PC, KS) + 1024 + 256;
+}
+
+template <int R, int PC, bool DEC>
+__global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_planar_kernel(const UmArgs a) {
+    constexpr int P = R;                     // D == 1: outputs per row
+    constexpr int MB = 32 / PC;              // 128-row blocks per tile
+    constexpr int N = 3 * PC;                // MMA N per plane: 3 digits x PC candidates
+    constexpr int TILE_ROWS = 128 * MB;
+    const int SB = a.stage_bytes, NST = a.stages, PB = SB / 2;  // stage = I plane, Q plane
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * UM_STAGES + 4];
+    __shared__ uint32_t tmem_base_s;
+    const FirArgs &f = a.f;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KS = a.KS;
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t stage0 = base;
+    const uint32_t tab_s = stage0 + NST * SB;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (UM_STAGES + s); };
+    auto accf_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + s); };
+    auto acce_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + 2 + s); };
+
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.tab);
+        uint4 *dst = reinterpret_cast<uint4 *>(gen + NST * SB);
+        for (int i = tid; i < KS * N * 2; i += UM_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full_bar(s), 32 * UM_PROD_WARPS); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == UM_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const long long nwork = (long long)a.ntiles * f.n_ch;
+    const long long wstride = gridDim.x;
+
+    if (warp < UM_PROD_WARPS) {
+        // ================= producers =================
+        // Every lane owns the chunks c = ptid + 96 i of each tile, end to end: cp.async them (two tiles ahead) into a
+        // raw ring slot, wait for its OWN copies (cp.async.wait_group), split each 16-byte chunk into 8 I + 8 Q bytes
+        // and store them into the stage's planes.  No producer-to-producer synchronisation, deep asynchronous loads.
+        const int ptid = warp * 32 + lane;
+        const int nchunks = (R * (TILE_ROWS - 1) + 32 * KS + 7) / 8;  // 8-sample chunks a tile touches
+        const int RAWB = 16 * nchunks;
+        uint8_t *raw0 = gen + (size_t)NST * SB + (size_t)KS * N * 32 + (size_t)16 * (DEC ? 6144 : 32 * 8 * 16);
+        auto issue = [&](long long w, int slot) {
+            if (w < nwork) {
+                const int ch = (int)(w / a.ntiles);
+                const long long w0 = f.first - (f.K - 1) - a.delta + (w % a.ntiles) * (long long)(TILE_ROWS * R);  // multiple of 8
+                const unsigned char *in = (const unsigned char *)f.in + (long long)ch * f.in_stride * 2;
+                const unsigned char *hist = (const unsigned char *)f.hist + (long long)ch * f.hist_stride * 2;
+                uint8_t *rs = raw0 + (size_t)slot * RAWB;
+                const uint32_t rs_s = smem_u32(rs);
+                if (w0 >= 0 && w0 + 8LL * nchunks <= f.n_in) {
+                    const unsigned char *src = in + 2 * w0;
+#pragma unroll 4
+                    for (int c = ptid; c < nchunks; c += 32 * UM_PROD_WARPS) cp_async16_s(rs_s + 16u * c, src + 16 * c);
+                } else {
+                    for (int c = ptid; c < nchunks; c += 32 * UM_PROD_WARPS) {
+                        const long long s0 = w0 + 8LL * c;
+                        if (s0 >= 0 && s0 + 8 <= f.n_in) {
+                            cp_async16_s(rs_s + 16u * c, in + 2 * s0);
+                        } else if (s0 < f.n_in) {
+                            // stream start (carried history, then "zero" samples = byte pair 128,128) or the ragged end
+                            unsigned short h[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const long long s = s0 + i;
+                                unsigned short v = 0x8080;
+                                if (s >= 0) { if (s < f.n_in) v = *reinterpret_cast<const unsigned short *>(in + 2 * s); }
+                                else if (s >= -(long long)f.HL) v = *reinterpret_cast<const unsigned short *>(hist + 2 * ((long long)f.HL + s));
+                                h[i] = v;
+                            }
+                            uint4 q;
+                            q.x = h[0] | ((unsigned)h[1] << 16); q.y = h[2] | ((unsigned)h[3] << 16);
+                            q.z = h[4] | ((unsigned)h[5] << 16); q.w = h[6] | ((unsigned)h[7] << 16);
+                            *reinterpret_cast<uint4 *>(rs + 16 * c) = q;  // read back by this same lane
+                        }
+                        // chunks entirely past the end feed only rows whose outputs are never stored: left as they are
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        issue(blockIdx.x, 0);
+        issue(blockIdx.x + wstride, 1);
+        int stage = 0, slot = 0;
+        uint32_t ph = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride) {
+            int s2 = slot + 2;
+            if (s2 >= UM_RAW_SLOTS) s2 -= UM_RAW_SLOTS;
+            issue(w + 2 * wstride, s2);
+            asm volatile("cp.async.wait_group 2;" ::: "memory");  // this lane's chunks of tile w have landed
+            mbar_wait(empty_bar(stage), ph ^ 1u);
+            uint8_t *pI = gen + (size_t)stage * SB, *pQ = pI + PB;
+            const uint8_t *rs = raw0 + (size_t)slot * RAWB;
+#pragma unroll 2
+            for (int c = ptid; c < nchunks; c += 32 * UM_PROD_WARPS) {
+                const uint4 q = *reinterpret_cast<const uint4 *>(rs + 16 * c);  // words = I0 Q0 I1 Q1
+                const uint32_t i_lo = __byte_perm(q.x, q.y, 0x6420), i_hi = __byte_perm(q.z, q.w, 0x6420);
+                const uint32_t q_lo = __byte_perm(q.x, q.y, 0x7531), q_hi = __byte_perm(q.z, q.w, 0x7531);
+                const uint32_t off = PitchLayout<R>::swz((8u * (uint32_t)c) & ~15u) | ((8u * (uint32_t)c) & 8u);
+                *reinterpret_cast<uint2 *>(pI + off) = make_uint2(i_lo, i_hi);
+                *reinterpret_cast<uint2 *>(pQ + off) = make_uint2(q_lo, q_hi);
+            }
+            fence_proxy_async();  // plain stores -> visible to the tensor core's (async proxy) operand reads
+            mbar_arrive(full_bar(stage));
+            if (++stage == NST) { stage = 0; ph ^= 1u; }
+            if (++slot == UM_RAW_SLOTS) slot = 0;
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (warp == UM_MMA_WARP) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t bdesc0 = smem_desc(tab_s, 128, 256, 0);
+        int stage = 0, as = 0;
+        uint32_t ph = 0, aph = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride) {
+            mbar_wait(full_bar(stage), ph);
+            mbar_wait(acce_bar(as), aph ^ 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint64_t aI = smem_desc(stage0 + (uint32_t)stage * SB, 16, 8 * R, PitchLayout<R>::type);
+                const uint64_t aQ = smem_desc(stage0 + (uint32_t)stage * SB + PB, 16, 8 * R, PitchLayout<R>::type);
+                const uint32_t d0 = tmem + (uint32_t)(as * UM_ACC_COLS);
+                for (int kk = 0; kk < KS; ++kk) {
+                    const uint64_t bd = bdesc0 + (uint64_t)((kk * N * 32) >> 4);
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb) {
+                        const uint64_t ao = (uint64_t)((mb * 128 * R + kk * 32) >> 4);
+                        umma_i8(d0 + mb * 2 * N, aI + ao, bd, idesc, kk > 0);
+                        umma_i8(d0 + mb * 2 * N + N, aQ + ao, bd, idesc, kk > 0);
+                    }
+                }
+                umma_commit(empty_bar(stage));
+                umma_commit(accf_bar(as));
+            }
+            __syncwarp();
+            if (++stage == NST) { stage = 0; ph ^= 1u; }
+            as ^= 1;
+            if (as == 0) aph ^= 1u;
+        }
+    } else {
+        // ================= epilogue (see fir_umma_kernel) =================
+        const int ew = warp - UM_EPI_WARP0, wg = ew >> 2, g = wg & 1, h = wg >> 1;
+        const int quad = warp & 3;
+        constexpr int PPB = PC / 8;
+        constexpr int SW = 8;  // P >= 16 always here
+        constexpr int STG_BYTES = DEC ? 6144 : 32 * SW * 16;
+        uint8_t *stg = gen + (size_t)NST * SB + (size_t)KS * N * 32 + (size_t)ew * STG_BYTES;
+        const float sc0 = a.sc[0], sc2 = a.sc[2];
+        const int c10 = a.magic[0][0], m2 = a.magic[0][2];
+        uint32_t aph = 0;
+        long long it = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
+            if ((it & 1) != g) continue;
+            const int ch = (int)(w / a.ntiles);
+            const long long row0 = (w % a.ntiles) * (long long)TILE_ROWS;
+            float2 *out = (float2 *)f.out + (long long)ch * f.out_stride;
+            mbar_wait(accf_bar(g), aph);
+            aph ^= 1u;
+            tc_fence_after();
+            const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * UM_ACC_COLS);
+            long long pos0 = 0, m_lo = 0;
+            int n_m = 0;
+#pragma unroll
+            for (int pj = 0; pj < 2; ++pj) {
+                const int pi = 2 * h + pj, mb = pi / PPB, pc = pi % PPB;
+                uint32_t dI[3][8], dQ[3][8];
+                {
+                    const uint32_t col = tbase + (uint32_t)(mb * 2 * N + 8 * pc);
+#pragma unroll
+                    for (int dg = 0; dg < 3; ++dg) {
+                        tmem_ld8(col + dg * PC, dI[dg]);
+                        tmem_ld8(col + N + dg * PC, dQ[dg]);
+                    }
+                    tmem_ld_wait();
+                }
+                if (pj == 1) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(acce_bar(g));
+                }
+                if constexpr (DEC) {
+                    constexpr int G = R / PC, LG = (G == 1) ? 0 : (G == 2) ? 1 : 2;
+                    uint4 *srow = reinterpret_cast<uint4 *>(stg) + lane * 12;
+#pragma unroll
+                    for (int dg = 0; dg < 3; ++dg)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            int c = dg * 4 + q + (lane % 12);
+                            if (c >= 12) c -= 12;
+                            srow[c] = make_uint4(dI[dg][2 * q], dQ[dg][2 * q], dI[dg][2 * q + 1], dQ[dg][2 * q + 1]);
+                        }
+                    __syncwarp();
+                    if (pj == 0 || PPB == 1) {
+                        pos0 = (row0 + mb * 128 + quad * 32) * (long long)R;
+                        m_lo = (pos0 + f.D - 1) / f.D;
+                        n_m = (int)((pos0 + 32 * R + f.D - 1) / f.D - m_lo);
+                    }
+                    for (int i = lane; i < n_m; i += 32) {
+                        const long long m = m_lo + i;
+                        const int pos = (int)(m * f.D - pos0);
+                        const int r = pos / R, u = (pos % R) >> LG;
+                        if ((u >> 3) == pc && m < f.n_out) {
+                            const int uu = u & 7, cb = uu >> 1, rot = r % 12;
+                            const unsigned char *rowp = stg + r * 192 + (uu & 1) * 8;
+                            int c0 = cb + rot, c1 = 4 + cb + rot, c2 = 8 + cb + rot;
+                            if (c0 >= 12) c0 -= 12;
+                            if (c1 >= 12) c1 -= 12;
+                            if (c2 >= 12) c2 -= 12;
+                            const uint2 a0 = *reinterpret_cast<const uint2 *>(rowp + c0 * 16);
+                            const uint2 a1 = *reinterpret_cast<const uint2 *>(rowp + c1 * 16);
+                            const uint2 a2 = *reinterpret_cast<const uint2 *>(rowp + c2 * 16);
+                            const float fI = (float)((int)(a1.x << 8) + (int)a0.x + c10);
+                            const float fQ = (float)((int)(a1.y << 8) + (int)a0.y + c10);
+                            const float gI = __int_as_float((int)a2.x + m2) - 12582912.0f;
+                            const float gQ = __int_as_float((int)a2.y + m2) - 12582912.0f;
+                            out[m] = make_float2(fmaf(gI, sc2, fI * sc0), fmaf(gQ, sc2, fQ * sc0));
+                        }
+                    }
+                    __syncwarp();
+                } else {
+                    float y[16];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float fI = (float)((int)(dI[1][u] << 8) + (int)dI[0][u] + c10);
+                        const float fQ = (float)((int)(dQ[1][u] << 8) + (int)dQ[0][u] + c10);
+                        const float gI = __int_as_float((int)dI[2][u] + m2) - 12582912.0f;
+                        const float gQ = __int_as_float((int)dQ[2][u] + m2) - 12582912.0f;
+                        y[2 * u] = fmaf(gI, sc2, fI * sc0);
+                        y[2 * u + 1] = fmaf(gQ, sc2, fQ * sc0);
+                    }
+                    const int cl0 = 4 * (pc % (SW / 4));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const int c = cl0 + q;
+                        *reinterpret_cast<float4 *>(stg + ((size_t)lane * SW + (c ^ (lane & 7))) * 16) =
+                            make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                    }
+                    if (cl0 + 4 == SW) {
+                        __syncwarp();
+                        const int phase0 = (P == 32) ? 16 * h : 0;
+                        const long long mrow = (row0 + mb * 128 + quad * 32) * (long long)P;
+                        float4 val[SW];
+#pragma unroll
+                        for (int i = 0; i < SW; ++i) {
+                            const int q = i * 32 + lane;
+                            const int row = q / SW, c = q % SW;
+                            val[i] = *reinterpret_cast<const float4 *>(stg + ((size_t)row * SW + (c ^ (row & 7))) * 16);
+                        }
+                        if (mrow + 32 * P <= f.n_out) {
+#pragma unroll
+                            for (int i = 0; i < SW; ++i) {
+                                const int q = i * 32 + lane;
+                                *reinterpret_cast<float4 *>(out + mrow + (q / SW) * P + phase0 + 2 * (q % SW)) = val[i];
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < SW; ++i) {
+                                const int q = i * 32 + lane;
+                                const long long m = mrow + (long long)(q / SW) * P + phase0 + 2 * (q % SW);
+                                if (m + 1 < f.n_out) *reinterpret_cast<float4 *>(out + m) = val[i];
+                                else if (m < f.n_out) out[m] = make_float2(val[i].x, val[i].y);
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == UM_MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+    }
+}
+
 // balanced base-256 digits of t: t = d0 + 256 d1 + 65536 d2, d0, d1 in [-128, 127]; false if d2 leaves that range
 inline bool digits3(long long t, int d[3]) {
     for (int i = 0; i < 2; ++i) {
@@ -420,14 +748,33 @@ static int gcd_i(int a, int b) { while (b) { const int t = a % b; a = b; b = t; 
 // k-steps of 16 samples: a row's window spans K + 7 (alignment) + the largest candidate offset R - g samples
 int fir_umma_ksteps(int K, int R, int PC) { return (K + 7 + R - R / PC + 15) / 16; }
 
-// geometry for (K, D): row pitch R and candidates per row PC; false if the tcgen05 path does not apply
-bool fir_umma_geometry(int K, int D, int *R_out, int *PC_out) {
+int fir_umma_planar_ksteps(int K, int R, int PC) { return (K + 7 + R - R / PC + 31) / 32; }
+
+// geometry for (K, D, tap kind): row pitch R, candidates per row PC, planar (real taps) or interleaved stages;
+// false if the tcgen05 path does not apply
+bool fir_umma_geometry(int K, int D, bool taps_complex, bool want_planar, int *R_out, int *PC_out, int *planar_out) {
     if (K < 1 || K > UM_MAX_K || D < 1) return false;
+    const char *e = std::getenv("SDR_UMMA_P");
+    const int forced = e ? std::atoi(e) : 0;
+    *planar_out = 0;
+    if (!taps_complex && want_planar) {
+        // real taps: byte planes, rows R bytes = R samples apart
+        int R = 0, PC = 0;
+        if (D == 1) {
+            R = PC = (forced == 16) ? 16 : 32;
+        } else if (64 / gcd_i(D, 64) == 16 || 64 / gcd_i(D, 64) == 32) {
+            R = 64; PC = 64 / gcd_i(D, 64);
+        } else if (32 / gcd_i(D, 32) == 16 || 32 / gcd_i(D, 32) == 32) {
+            R = 32; PC = 32 / gcd_i(D, 32);
+        }
+        if (R && um_planar_smem_bytes(R, PC, fir_umma_planar_ksteps(K, R, PC), D != 1, 2) <= 220 * 1024) {
+            *R_out = R; *PC_out = PC; *planar_out = 1;
+            return true;
+        }
+    }
     if (D == 1) {
         int best = 0;
         double best_c = 1e30;
-        const char *e = std::getenv("SDR_UMMA_P");
-        const int forced = e ? std::atoi(e) : 0;
         for (int p : {8, 16, 32}) {
             const int ks = fir_umma_ksteps(K, p, p);
             if (um_smem_bytes(p, p, ks, false, 2) > 220 * 1024) continue;
@@ -451,9 +798,9 @@ bool fir_umma_geometry(int K, int D, int *R_out, int *PC_out) {
 // host: the 8 alignment variants of the Toeplitz tap table.  Layout [delta][kk][canonical N x 32 B block]:
 // element (n, kb) of a block sits at (n/8)*256 + (kb/16)*128 + (n%8)*16 + kb%16 (no-swizzle K-major core matrices).
 // Column n = digit * 2 PC + 2 u + part; candidate u is the output whose oldest sample sits g*u (+ delta) into the row.
-bool fir_umma_build_tables(const float *taps, int K, bool tc, int R, int PC, std::vector<uint8_t> &out, int magic[2][3], float sc[3]) {
-    if (K < 1 || K > UM_MAX_K) return false;
-    const int KS = fir_umma_ksteps(K, R, PC), N = 6 * PC, W = tc ? 2 : 1, G = R / PC;
+bool fir_umma_build_tables(const float *taps, int K, bool tc, int R, int PC, bool planar, std::vector<uint8_t> &out, int magic[2][3], float sc[3]) {
+    if (K < 1 || K > UM_MAX_K || (planar && tc)) return false;
+    const int KS = planar ? fir_umma_planar_ksteps(K, R, PC) : fir_umma_ksteps(K, R, PC), N = (planar ? 3 : 6) * PC, W = tc ? 2 : 1, G = R / PC;
     float cmax = 0.0f;
     for (int i = 0; i < K * W; ++i) {
         if (!std::isfinite(taps[i])) return false;
@@ -501,9 +848,11 @@ bool fir_umma_build_tables(const float *taps, int K, bool tc, int R, int PC, std
         for (int kk = 0; kk < KS; ++kk) {
             uint8_t *blk = out.data() + ((size_t)delta * KS + kk) * N * 32;
             for (int n = 0; n < N; ++n) {
-                const int dg = n / (2 * PC), u = (n % (2 * PC)) / 2, part = n & 1;
+                // interleaved: column (digit, candidate, part), byte kb = sample kb/2, part kb&1
+                // planar:      column (digit, candidate),       byte kb = sample kb of the plane
+                const int dg = planar ? n / PC : n / (2 * PC), u = planar ? n % PC : (n % (2 * PC)) / 2, part = planar ? 0 : (n & 1);
                 for (int kb = 0; kb < 32; ++kb) {
-                    const int s = kk * 16 + kb / 2, q = kb & 1;
+                    const int s = planar ? kk * 32 + kb : kk * 16 + kb / 2, q = planar ? 0 : (kb & 1);
                     const int k = K - 1 + delta + G * u - s;
                     int v = 0;
                     if (k >= 0 && k < K) v = digit(k, part, q, dg);
@@ -515,18 +864,19 @@ bool fir_umma_build_tables(const float *taps, int K, bool tc, int R, int PC, std
 }
 
 // returns SDR_ERR_UNSUPPORTED when this path does not apply (caller falls back to the mma.sync / CUDA-core kernels)
-int fir_umma_launch(const FirArgs &f, int R, int PC, const uint8_t *d_tables, const int magic[2][3], const float sc[3], cudaStream_t st) {
+int fir_umma_launch(const FirArgs &f, int R, int PC, bool planar, const uint8_t *d_tables, const int magic[2][3], const float sc[3], cudaStream_t st) {
     if (f.n_out <= 0) return SDR_OK;
-    if (f.K > UM_MAX_K || (f.D == 1 && R != PC) || (f.D != 1 && R != 32)) return SDR_ERR_UNSUPPORTED;
+    if (f.K > UM_MAX_K || (f.D == 1 && R != PC) || (f.D != 1 && !planar && R != 32)) return SDR_ERR_UNSUPPORTED;
     // rows of a multi-channel call must keep the 16-byte alignment of the first one (strides are ignored for one channel)
     if (((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 15) || ((uintptr_t)f.hist & 1) ||
         (f.n_ch > 1 && ((f.out_stride & 1) || (f.in_stride & 7))))
         return SDR_ERR_UNSUPPORTED;
     const bool dec = f.D != 1;
-    const int KS = fir_umma_ksteps(f.K, R, PC);
+    const int KS = planar ? fir_umma_planar_ksteps(f.K, R, PC) : fir_umma_ksteps(f.K, R, PC);
+    auto smem_of = [&](int st_) { return planar ? um_planar_smem_bytes(R, PC, KS, dec, st_) : um_smem_bytes(R, PC, KS, dec, st_); };
     int stages = UM_STAGES;
-    while (stages > 2 && um_smem_bytes(R, PC, KS, dec, stages) > 220 * 1024) --stages;
-    const size_t smem = um_smem_bytes(R, PC, KS, dec, stages);
+    while (stages > 2 && smem_of(stages) > 220 * 1024) --stages;
+    const size_t smem = smem_of(stages);
     if (smem > 220 * 1024) return SDR_ERR_UNSUPPORTED;
     UmArgs a;
     a.stages = stages;
@@ -535,8 +885,8 @@ int fir_umma_launch(const FirArgs &f, int R, int PC, const uint8_t *d_tables, co
     long long d = (f.first - (f.K - 1)) % 8;
     if (d < 0) d += 8;
     a.delta = (int)d;
-    a.tab = d_tables + (size_t)d * KS * 6 * PC * 32;
-    a.stage_bytes = um_stage_bytes(R, PC, KS);
+    a.tab = d_tables + (size_t)d * KS * (planar ? 3 : 6) * PC * 32;
+    a.stage_bytes = planar ? 2 * um_plane_bytes(R, PC, KS) : um_stage_bytes(R, PC, KS);
     a.n_rows = ((f.n_out - 1) * (long long)f.D) / R + 1;
     const int tile_rows = 128 * (32 / PC);
     a.ntiles = (int)((a.n_rows + tile_rows - 1) / tile_rows);
@@ -558,6 +908,15 @@ int fir_umma_launch(const FirArgs &f, int R, int PC, const uint8_t *d_tables, co
         count_launch();
         return launch_status();
     };
+    if (planar) {
+        if (!dec && R == 16) return go(fir_umma_planar_kernel<16, 16, false>);
+        if (!dec && R == 32) return go(fir_umma_planar_kernel<32, 32, false>);
+        if (dec && R == 64 && PC == 16) return go(fir_umma_planar_kernel<64, 16, true>);
+        if (dec && R == 64 && PC == 32) return go(fir_umma_planar_kernel<64, 32, true>);
+        if (dec && R == 32 && PC == 16) return go(fir_umma_planar_kernel<32, 16, true>);
+        if (dec && R == 32 && PC == 32) return go(fir_umma_planar_kernel<32, 32, true>);
+        return SDR_ERR_UNSUPPORTED;
+    }
     if (!dec) {
         switch (R) {
             case 8: return go(fir_umma_kernel<8, 8, false>);
