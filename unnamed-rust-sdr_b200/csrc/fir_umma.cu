@@ -25,16 +25,16 @@
 // Decimation (signal::Decimate fused behind the filter, src/signal/adapters/mod.rs:30-37): rows stay R = 32 samples
 // apart (a matrix descriptor cannot step by D), and the B columns are the CANDIDATE offsets inside a row at which a
 // kept output can fall: kept output m sits D*m samples after output 0, i.e. in row (D m) div R at offset (D m) mod R, a
-// multiple of g = gcd(D, R).  Only those R/g offsets get columns (D = 10: 16 of 32, N = 96), the epilogue converts and
-// stores the ones that are kept outputs (compare against a running "next kept position", no division per candidate).
+// multiple of g = gcd(D, R).  Only those R/g offsets get columns (D = 10: 16 of 32, N = 96); the epilogue keeps a
+// candidate iff its offset from output 0 is a multiple of D (multiply-shift modulo) and stores it at out[offset / D].
 //
-// Warp roles (one persistent CTA per SM, 320 threads):
-//   warp 0      producer: cp.async 16-byte chunks global -> (swizzled) stage, completion on an mbarrier
+// Warp roles (one persistent CTA per SM, 640 threads):
+//   warps 0..2  producers: cp.async 16-byte chunks global -> (swizzled) stage, completion on an mbarrier
 //                          (cp.async.mbarrier.arrive.noinc); history / zero padding at the stream start by plain stores
-//   warp 1      MMA issuer: one lane issues KS * MB tcgen05.mma.kind::i8 per tile, tcgen05.commit frees the stage and
+//   warp 3      MMA issuer: one lane issues KS * MB tcgen05.mma.kind::i8 per tile, tcgen05.commit frees the stage and
 //                          publishes the accumulator set
-//   warps 2..9  two epilogue warpgroups (one per accumulator set): tcgen05.ld -> digits -> f32 -> XOR-swizzled
-//               warp-private staging -> 512-byte coalesced global stores
+//   warps 4..19 four epilogue warpgroups (two accumulator sets x two halves of a tile): tcgen05.ld.16x256b fragments ->
+//               digits -> f32 -> global stores straight from registers (4 threads = one 32-byte sector)
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -64,6 +64,7 @@ struct UmArgs {
     int stage_bytes;     // one stage: the tile's window starts + (KS*32 B) halo, multiple of 1024 (swizzle period)
     long long n_rows;    // window rows per channel that hold at least one kept output
     int stages;          // input stages in the ring (2..UM_STAGES)
+    unsigned dmagic;     // floor(2^32 / D) + 1: n / D == umulhi(n, dmagic) for n < 2^17, D <= 4096
     int magic[2][3];     // [part]: {-(256 C1 + C0), unused, 0x4B400000 - C2}, C_d = 128 * sum of that column's digit-d taps
     float sc[3];         // 2^-(S+7) * {1, 256, 65536}
 };
@@ -98,10 +99,12 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
                  ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+// 16 lanes x 256 bits, twice: thread t gets, for column groups cg = 0, 1 (8 columns each), the column pair
+// 8 cg + 2 (t%4), +1 of lane t/4 (regs 4cg, 4cg+1) and of lane t/4 + 8 (regs 4cg+2, 4cg+3) -- the mma accumulator
+// fragment layout: 4 consecutive threads hold 4 consecutive (I, Q) column pairs of one row = 32 contiguous output bytes
+__device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -122,8 +125,9 @@ __host__ __device__ constexpr int um_stage_bytes(int R, int PC, int KS) {
     return (2 * R * (128 * (32 / PC) - 1) + 32 * KS + 1023) / 1024 * 1024;
 }
 __host__ __device__ constexpr size_t um_smem_bytes(int R, int PC, int KS, bool dec, int stages = UM_STAGES) {
-    // tables + stages + epilogue staging (16 warps x 32 rows x 64 / 128 B; decimating: x 192 B) + 1 KB slack + barriers
-    return (size_t)KS * 6 * PC * 32 + (size_t)stages * um_stage_bytes(R, PC, KS) + (dec ? (size_t)16 * 6144 : (size_t)16 * 32 * (R >= 16 ? 8 : 4) * 16) + 1024 + 256;
+    // tables + stages + 1 KB alignment slack + barriers (the epilogue stores straight from registers)
+    (void)dec;
+    return (size_t)KS * 6 * PC * 32 + (size_t)stages * um_stage_bytes(R, PC, KS) + 1024 + 256;
 }
 
 // R = samples between window rows (8 / 16 / 32: no / 32-byte / 64-byte swizzle), PC = output candidates per row
@@ -262,9 +266,6 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
         const int ew = warp - UM_EPI_WARP0, wg = ew >> 2, g = wg & 1, h = wg >> 1;
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
         constexpr int PPB = PC / 8;                  // pieces per 128-row block
-        constexpr int SW = (P >= 16 ? 16 : 8) / 2;   // 16-byte chunks per staged row: the warp's share of an output row
-        constexpr int STG_BYTES = DEC ? 6144 : 32 * SW * 16;
-        uint8_t *stg = gen + (size_t)NST * SB + (size_t)KS * N * 32 + (size_t)ew * STG_BYTES;
         const float sc0 = a.sc[0], sc2 = a.sc[2];
         const int c10[2] = {a.magic[0][0], a.magic[1][0]}, m2[2] = {a.magic[0][2], a.magic[1][2]};
         uint32_t aph = 0;
@@ -278,118 +279,65 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
             aph ^= 1u;
             tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * UM_ACC_COLS);
-            long long pos0 = 0, m_lo = 0;  // DEC: sample offset of the warp's 32-row span, first kept output inside it
-            int n_m = 0;                   // DEC: kept outputs inside it
+            // DEC: kept output m sits at sample offset D*m from output 0; the tile starts at offset row0*R
+            unsigned rem0 = 0;
+            long long mt0 = 0;
+            if constexpr (DEC) {
+                const long long tp = row0 * (long long)R;
+                mt0 = tp / f.D;
+                rem0 = (unsigned)(tp - mt0 * f.D);
+            }
 #pragma unroll
             for (int pj = 0; pj < 2; ++pj) {
                 const int pi = 2 * h + pj, mb = pi / PPB, pc = pi % PPB;
-                uint32_t d[3][16];
-                {
-                    const uint32_t col = tbase + (uint32_t)(mb * N + 16 * pc);
-                    tmem_ld16(col, d[0]);
-                    tmem_ld16(col + 2 * PC, d[1]);
-                    tmem_ld16(col + 4 * PC, d[2]);
-                    tmem_ld_wait();
-                }
+                // No shared-memory staging: the 16x256b fragment shape hands every thread whole (I, Q) column pairs of
+                // two rows; 4 neighbouring threads hold 4 consecutive candidates of one row.  D == 1: 32 contiguous
+                // output bytes (one full sector) per 4 threads, 8 sectors per store instruction.  The shared-memory
+                // port is left to the MMA operand fetch and the producers.
+                uint32_t e[2][3][8];
+                const uint32_t col = tbase + (uint32_t)(mb * N + 16 * pc);
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                    for (int dg = 0; dg < 3; ++dg) tmem_ld_16x256b_x2(col + ((uint32_t)(16 * hh) << 16) + dg * 2 * PC, e[hh][dg]);
+                tmem_ld_wait();
                 if (pj == 1) {
                     // this warp's share of the set is in registers: hand it back to the MMA warp (8 warps arrive)
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acce_bar(g));
                 }
-                if constexpr (DEC) {
-                    // Only ~R/D of a row's candidates are kept outputs, at lane-dependent places.  The piece's raw
-                    // accumulators (8 candidates x 3 digits x (I, Q) = 48 words = 12 chunks per row) go to the warp's
-                    // staging tile (chunk (c + row) mod 12: conflict-free), then the lanes walk the kept outputs of
-                    // the warp's 32-row span -- consecutive m, so conversion work and stores are dense.
-                    constexpr int G = R / PC, LG = (G == 1) ? 0 : (G == 2) ? 1 : 2;
-                    uint4 *srow = reinterpret_cast<uint4 *>(stg) + lane * 12;
 #pragma unroll
-                    for (int dg = 0; dg < 3; ++dg)
+                for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            int c = dg * 4 + q + (lane % 12);
-                            if (c >= 12) c -= 12;
-                            srow[c] = make_uint4(d[dg][4 * q], d[dg][4 * q + 1], d[dg][4 * q + 2], d[dg][4 * q + 3]);
-                        }
-                    __syncwarp();
-                    if (pj == 0 || PPB == 1) {
-                        pos0 = (row0 + mb * 128 + quad * 32) * (long long)R;  // first sample offset of the warp's span
-                        m_lo = (pos0 + f.D - 1) / f.D;                        // first kept output inside it
-                        n_m = (int)((pos0 + 32 * R + f.D - 1) / f.D - m_lo);  // kept outputs inside it
-                    }
-                    for (int i = lane; i < n_m; i += 32) {
-                        const long long m = m_lo + i;
-                        const int pos = (int)(m * f.D - pos0);
-                        const int r = pos / R, u = (pos % R) >> LG;
-                        if ((u >> 3) == pc && m < f.n_out) {
-                            const int uu = u & 7, cb = uu >> 1, rot = r % 12;
-                            const unsigned char *rowp = stg + r * 192 + (uu & 1) * 8;
-                            int c0 = cb + rot, c1 = 4 + cb + rot, c2 = 8 + cb + rot;
-                            if (c0 >= 12) c0 -= 12;
-                            if (c1 >= 12) c1 -= 12;
-                            if (c2 >= 12) c2 -= 12;
-                            const uint2 a0 = *reinterpret_cast<const uint2 *>(rowp + c0 * 16);
-                            const uint2 a1 = *reinterpret_cast<const uint2 *>(rowp + c1 * 16);
-                            const uint2 a2 = *reinterpret_cast<const uint2 *>(rowp + c2 * 16);
-                            const float fI = (float)((int)(a1.x << 8) + (int)a0.x + c10[0]);
-                            const float fQ = (float)((int)(a1.y << 8) + (int)a0.y + c10[1]);
-                            const float gI = __int_as_float((int)a2.x + m2[0]) - 12582912.0f;
-                            const float gQ = __int_as_float((int)a2.y + m2[1]) - 12582912.0f;
-                            out[m] = make_float2(fmaf(gI, sc2, fI * sc0), fmaf(gQ, sc2, fQ * sc0));
-                        }
-                    }
-                    __syncwarp();
-                } else {
-                    float y[16];
+                    for (int cg = 0; cg < 2; ++cg)
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        // digits 0 and 1 combine exactly in s32 ((A1 << 8) + A0, |.| < 2^31 for K <= 511; wrap-around
-                        // safe); digit 2 (|A2| < 2^23) converts with the 1.5 * 2^23 magic add: one I2F per value
-                        const float f10 = (float)((int)(d[1][i] << 8) + (int)d[0][i] + c10[i & 1]);
-                        const float f2 = __int_as_float((int)d[2][i] + m2[i & 1]) - 12582912.0f;
-                        y[i] = fmaf(f2, sc2, f10 * sc0);
-                    }
-                    // row `lane` of the warp's staging tile (SW chunks per row), XOR-swizzled: conflict-free both ways
-                    const int cl0 = 4 * (pc % (SW / 4));
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int c = cl0 + q;
-                        const int pcn = (SW == 4) ? (c ^ ((lane >> 1) & 3)) : (c ^ (lane & 7));
-                        *reinterpret_cast<float4 *>(stg + ((size_t)lane * SW + pcn) * 16) =
-                            make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
-                    }
-                    if (cl0 + 4 == SW) {
-                        __syncwarp();
-                        // the warp's 32 (sub-)rows: row r holds outputs (row index)*P + phase0 .. + 2 SW - 1
-                        const int phase0 = (P == 32) ? 16 * h : 0;
-                        const long long mrow = (row0 + mb * 128 + quad * 32) * (long long)P;
-                        float4 val[SW];
-#pragma unroll
-                        for (int i = 0; i < SW; ++i) {
-                            const int q = i * 32 + lane;
-                            const int row = q / SW, c = q % SW;
-                            const int pcn = (SW == 4) ? (c ^ ((row >> 1) & 3)) : (c ^ (row & 7));
-                            val[i] = *reinterpret_cast<const float4 *>(stg + ((size_t)row * SW + pcn) * 16);
-                        }
-                        if (mrow + 32 * P <= f.n_out) {
-#pragma unroll
-                            for (int i = 0; i < SW; ++i) {
-                                const int q = i * 32 + lane;
-                                *reinterpret_cast<float4 *>(out + mrow + (q / SW) * P + phase0 + 2 * (q % SW)) = val[i];
+                        for (int rs = 0; rs < 2; ++rs) {
+                            const int i0 = 4 * cg + 2 * rs;
+                            const int row = mb * 128 + quad * 32 + 16 * hh + 8 * rs + (lane >> 2);  // row inside the tile
+                            const int u = 8 * pc + 4 * cg + (lane & 3);                              // candidate
+                            long long m;
+                            bool keep;
+                            if constexpr (DEC) {
+                                // offset of this candidate from output 0, modulo D by multiply-shift (n < 2^17, D <= 4096)
+                                const unsigned n = rem0 + (unsigned)(row * R + (R / PC) * u);
+                                const unsigned q = __umulhi(n, a.dmagic);
+                                m = mt0 + q;
+                                keep = (n - q * (unsigned)f.D == 0u) && m < f.n_out;
+                            } else {
+                                m = (row0 + row) * (long long)P + u;
+                                keep = m < f.n_out;
                             }
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < SW; ++i) {
-                                const int q = i * 32 + lane;
-                                const long long m = mrow + (long long)(q / SW) * P + phase0 + 2 * (q % SW);
-                                if (m + 1 < f.n_out) *reinterpret_cast<float4 *>(out + m) = val[i];
-                                else if (m < f.n_out) out[m] = make_float2(val[i].x, val[i].y);
+                            if (keep) {
+                                // digits 0 and 1 combine exactly in s32 ((A1 << 8) + A0, |.| < 2^31 for K <= 511; wrap-around
+                                // safe); digit 2 (|A2| < 2^23) converts with the 1.5 * 2^23 magic add: one I2F per value
+                                const float fI = (float)((int)(e[hh][1][i0] << 8) + (int)e[hh][0][i0] + c10[0]);
+                                const float fQ = (float)((int)(e[hh][1][i0 + 1] << 8) + (int)e[hh][0][i0 + 1] + c10[1]);
+                                const float gI = __int_as_float((int)e[hh][2][i0] + m2[0]) - 12582912.0f;
+                                const float gQ = __int_as_float((int)e[hh][2][i0 + 1] + m2[1]) - 12582912.0f;
+                                out[m] = make_float2(fmaf(gI, sc2, fI * sc0), fmaf(gQ, sc2, fQ * sc0));
                             }
                         }
-                        __syncwarp();
-                    }
-                }
             }
         }
     }
@@ -753,7 +701,7 @@ int fir_umma_planar_ksteps(int K, int R, int PC) { return (K + 7 + R - R / PC + 
 // geometry for (K, D, tap kind): row pitch R, candidates per row PC, planar (real taps) or interleaved stages;
 // false if the tcgen05 path does not apply
 bool fir_umma_geometry(int K, int D, bool taps_complex, bool want_planar, int *R_out, int *PC_out, int *planar_out) {
-    if (K < 1 || K > UM_MAX_K || D < 1) return false;
+    if (K < 1 || K > UM_MAX_K || D < 1 || D > 4096) return false;
     const char *e = std::getenv("SDR_UMMA_P");
     const int forced = e ? std::atoi(e) : 0;
     *planar_out = 0;
@@ -890,6 +838,7 @@ int fir_umma_launch(const FirArgs &f, int R, int PC, bool planar, const uint8_t 
     a.n_rows = ((f.n_out - 1) * (long long)f.D) / R + 1;
     const int tile_rows = 128 * (32 / PC);
     a.ntiles = (int)((a.n_rows + tile_rows - 1) / tile_rows);
+    a.dmagic = (unsigned)((1ull << 32) / (unsigned long long)f.D + 1ull);
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 3; ++j) a.magic[i][j] = magic[i][j];
     for (int j = 0; j < 3; ++j) a.sc[j] = sc[j];
