@@ -346,13 +346,24 @@ struct Reg2Plan {
     static constexpr int RLAST = 1 << (LOGN - 4 * (NP - 1));  // radix of the last pass (16 if LOGN % 4 == 0)
     static constexpr int NBLAST = 16 / RLAST;
     // shared twiddle tables of the middle passes (pass j, 1 <= j <= NP-2): 15 * 16^j entries each
-    static constexpr int tab_entries() {
+    __host__ __device__ static constexpr int tab_entries() {
         int e = 0, p = 16;
         for (int j = 1; j <= NP - 2; ++j) { e += 15 * p; p *= 16; }
         return e;
     }
-    static constexpr size_t smem_bytes() { return ((size_t)SEQ * padlen(N) + tab_entries()) * sizeof(float2); }
+    // one transform per CTA: the NEXT transform's input is prefetched (cp.async) into a raw buffer while this one is
+    // computed, so a lone CTA per SM (n = 8192) still overlaps its HBM reads with its arithmetic
+    static constexpr bool PREFETCH = (SEQ == 1) && (LOGN >= 13);  // measured: +4 % at 8192, -5 % at 4096 (2 CTAs per SM already overlap)
+    __host__ __device__ static constexpr size_t raw_offset() { return (((size_t)SEQ * padlen(N) + tab_entries()) * sizeof(float2) + 15) / 16 * 16; }
+    __host__ __device__ static constexpr size_t smem_bytes(int elem_bytes) { return raw_offset() + (PREFETCH ? (size_t)N * elem_bytes : 0); }
 };
+template <int FMT> struct FmtBytes { static constexpr int v = FMT == SDR_FMT_U8IQ ? 2 : FMT == SDR_FMT_C64 ? 8 : 4; };
+template <int FMT>
+__device__ __forceinline__ float2 raw_elem(const unsigned char *raw, int idx) {
+    if (FMT == SDR_FMT_U8IQ) return unpack_iq_u16(*reinterpret_cast<const uint16_t *>(raw + 2 * idx));
+    if (FMT == SDR_FMT_C64) return *reinterpret_cast<const float2 *>(raw + 8 * idx);
+    return make_float2(*reinterpret_cast<const float *>(raw + 4 * idx), 0.0f);
+}
 
 // middle pass j (sub-size p = 16^j, radix 16): shared -> registers -> shared
 template <int LOGN, int PLOG>
@@ -408,13 +419,35 @@ fft_reg2_kernel(FftArgs a) {
 
     const bool shift = (a.flags & SDR_FFT_SHIFT) != 0 && !(a.flags & SDR_FFT_RFFT);
     const int out_len = (a.flags & SDR_FFT_RFFT) ? N - N / 2 : N;
+    constexpr bool PF = PL::PREFETCH;
+    constexpr int ES = FmtBytes<FMT>::v;
+    unsigned char *raw = reinterpret_cast<unsigned char *>(smem4) + PL::raw_offset();
+    auto issue_raw = [&](long long b) {
+        const unsigned char *src = reinterpret_cast<const unsigned char *>(a.in) + b * N * ES;
+#pragma unroll
+        for (int i = 0; i < (N * ES / 16 + THREADS - 1) / THREADS; ++i) {
+            const int q = tid + THREADS * i;
+            if (q < N * ES / 16) cp_async16(raw + 16 * q, src + 16 * q);
+        }
+        cp_async_commit();
+    };
+    if (PF && (long long)blockIdx.x < a.batches) issue_raw(blockIdx.x);
     for (long long b0 = (long long)blockIdx.x * SEQ; b0 < a.batches; b0 += (long long)gridDim.x * SEQ) {
         const long long b = b0 + group;
         const bool live = b < a.batches;
         float2 v[16];
-        // ---- pass 0: global -> registers, radix 16, no twiddles ----
+        // ---- pass 0: global (or the prefetched raw copy) -> registers, radix 16, no twiddles ----
+        if (PF) {
+            cp_async_wait<0>();
+            __syncthreads();
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = live ? load_elem<FMT>(a.in, b * N + t + e * TC) : make_float2(0.f, 0.f);
+            for (int e = 0; e < 16; ++e) v[e] = raw_elem<FMT>(raw, t + e * TC);
+            __syncthreads();  // the raw buffer is free: fetch the next transform behind this one's arithmetic
+            if (b0 + gridDim.x < a.batches) issue_raw(b0 + gridDim.x);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = live ? load_elem<FMT>(a.in, b * N + t + e * TC) : make_float2(0.f, 0.f);
+        }
         dft<16, 1>(v);
         if (NP == 1) {
             // (N == 16 is not dispatched here)
@@ -451,9 +484,13 @@ fft_reg2_kernel(FftArgs a) {
 }
 
 template <int LOGN, int FMT>
+int launch_cta(const FftArgs &a, cudaStream_t st);
+
+template <int LOGN, int FMT>
 int launch_reg2(const FftArgs &a, cudaStream_t st) {
     using PL = Reg2Plan<LOGN>;
-    const size_t smem = PL::smem_bytes();
+    const size_t smem = PL::smem_bytes(FmtBytes<FMT>::v);
+    if (PL::PREFETCH && (((uintptr_t)a.in) & 15)) return launch_cta<LOGN, FMT>(a, st);  // cp.async needs 16-byte rows
     auto kern = fft_reg2_kernel<LOGN, FMT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
