@@ -206,6 +206,32 @@ int sdr_pll_process_dev(sdr_pll_t *, const float *in_c64, size_t n, size_t in_st
 int sdr_pll_get_state(sdr_pll_t *, size_t stream_index, float *nphase, float *value_re, float *value_im);
 
 /* ======================================================================================
+ * Biquad as a stream filter -- Filter::apply of filter::Biquad<f32, A> (src/filter/biquad.rs:40-56)
+ * driven by signal::Filter (src/signal/adapters/mod.rs:94-96), e.g. the Lr de-emphasis filters of
+ * src/main.rs:52,75-80.  A = f32 or Complex<f32> (both parts filtered independently with the
+ * same real coefficients).  n_streams independent streams, one GPU lane per real sequence; the
+ * operation order of biquad.rs:44-49 is kept (no FMA), so results are bit-identical.
+ * ====================================================================================== */
+typedef struct {
+    const sdr_biquad_design_t *designs; /* n_designs entries */
+    size_t n_designs;                   /* 1 (shared by all streams) or n_streams */
+    size_t n_streams;
+    float rate;                         /* FilterDesign::design(rate), biquad.rs:83 */
+    int sample_complex;                 /* 0: Biquad<f32,f32>, 1: Biquad<f32,Complex<f32>> */
+    int device;
+    void *stream;
+} sdr_biquad_config_t;
+
+typedef struct sdr_biquad sdr_biquad_t;
+sdr_biquad_t *sdr_biquad_create(const sdr_biquad_config_t *cfg, int *err);
+void sdr_biquad_destroy(sdr_biquad_t *);
+int sdr_biquad_reset(sdr_biquad_t *);                        /* zero x1, x2, y1, y2 (Biquad::new, biquad.rs:25-38) */
+sdr_biquad_t *sdr_biquad_clone(const sdr_biquad_t *, int *err); /* #[derive(Clone)] biquad.rs:4 */
+/* in / out: n_streams rows of n samples (f32 or c64), row strides in samples (ignored for one stream) */
+int sdr_biquad_process(sdr_biquad_t *, const float *in, size_t n, size_t in_stride, float *out, size_t out_stride);
+int sdr_biquad_process_dev(sdr_biquad_t *, const float *in, size_t n, size_t in_stride, float *out, size_t out_stride);
+
+/* ======================================================================================
  * channelizer -- n_channels x ( Fir<f32,Complex<f32>> -> Pll ): config C4.  The FIR output
  * feeds the PLL on chip; only the PLL output leaves.  Same carried state as the two parts.
  * ====================================================================================== */

@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "../../oracle/sdr_oracle.h"
@@ -141,6 +142,25 @@ int main() {
         }
         EXPECT(mism <= 3 && e < 1e-3 * 1.8e6 * 0.035 * M_PI, "pll mismatches %zu err %g", mism, e);
         EXPECT(std::fabs(std::abs(pll.value()) - 1.0f) < 1e-6, "pll.value on the unit circle");
+    }
+
+    // ---- BiquadD::Lr(..).design(rate) as a stream filter (main.rs:75-80 de-emphasis): bit-identical to the reference order ----
+    {
+        std::vector<float> x(3000), want(3000);
+        for (size_t i = 0; i < x.size(); ++i) x[i] = (float)std::sin(0.013 * i) + 0.25f * (float)std::cos(0.31 * i);
+        filter::Biquad<float> bq(filter::BiquadD::Lr(1.0f / 75e-6f), 48000.0f);
+        std::vector<float> a, b;
+        bq.process(x.data(), 1234, a);
+        filter::Biquad<float> bq2(bq);  // clone keeps the state
+        bq.process(x.data() + 1234, x.size() - 1234, b);
+        std::vector<float> b2;
+        bq2.process(x.data() + 1234, x.size() - 1234, b2);
+        orc_biquad_t *ob = orc_biquad_new(ORC_BQ_LR, 1.0f / 75e-6f, 0.0f, 48000.0f, ORC_KIND_F32);
+        orc_biquad_apply(ob, x.data(), x.size(), want.data());
+        orc_biquad_free(ob);
+        a.insert(a.end(), b.begin(), b.end());
+        EXPECT(std::memcmp(a.data(), want.data(), want.size() * sizeof(float)) == 0, "biquad Lr bit-exact");
+        EXPECT(b == b2, "biquad clone");
     }
 
     // ---- Fir::apply per sample == block (filter/mod.rs:23-26) and clone keeps state ----

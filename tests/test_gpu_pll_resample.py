@@ -218,6 +218,42 @@ def test_c3_chain_matches_oracle_chain(sdr):
         assert np.abs(z - ref).max() <= 2e-7 * max(1.0, np.abs(ref).max())
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+def test_biquad_stream_filter_is_bit_identical_to_reference_order(sdr, cplx):
+    """Biquad<f32, A> as a stand-alone stream filter (biquad.rs:40-56; the Lr de-emphasis of main.rs:75-80 is one):
+    every BiquadD kind, f32 and Complex<f32> samples, ragged blocks, per-stream designs, clone / reset."""
+    B = sdr.BiquadD
+    rate = 48000.0
+    kinds = [(B.LowPass(3000.0, 0.7), (O.BQ_LOWPASS, 3000.0, 0.7)), (B.HighPass(500.0, 0.9), (O.BQ_HIGHPASS, 500.0, 0.9)),
+             (B.BandPass(19000.0, 5.0), (O.BQ_BANDPASS, 19000.0, 5.0)), (B.Notch(1000.0, 2.0), (O.BQ_NOTCH, 1000.0, 2.0)),
+             (B.Lr(1.0 / 75e-6), (O.BQ_LR, 1.0 / 75e-6, 0.0)), (B.Identity(), (O.BQ_IDENTITY, 0.0, 0.0))]
+    n = 5000
+    x = gen.complex_noise(n, 33) if cplx else gen.noise(n, 33).astype(np.float32)
+    for d, od in kinds:
+        want = O.biquad_apply(od[0], od[1], od[2], rate, x)
+        f = sdr.Biquad(d, rate, complex_samples=cplx)
+        cuts = [0, 1, 2, 33, 1000, 1031, n]
+        got = np.concatenate([f.process(x[a:b]) for a, b in zip(cuts[:-1], cuts[1:])])
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), d.kind
+    # one design per stream, 70 streams (more than two warps of sequences), clone mid-stream, reset
+    S_ = 70
+    designs = [kinds[i % 5][0] for i in range(S_)]
+    xs = (gen.complex_noise(S_ * 900, 5).reshape(S_, 900) if cplx else gen.noise(S_ * 900, 5).astype(np.float32).reshape(S_, 900))
+    f = sdr.Biquad(designs, rate, n_streams=S_, complex_samples=cplx)
+    a = f.process(np.ascontiguousarray(xs[:, :400]))
+    g = f.clone()
+    b = f.process(np.ascontiguousarray(xs[:, 400:]))
+    b2 = g.process(np.ascontiguousarray(xs[:, 400:]))
+    got = np.concatenate([a, b], 1)
+    for s_ in range(S_):
+        od = kinds[s_ % 5][1]
+        want = O.biquad_apply(od[0], od[1], od[2], rate, np.ascontiguousarray(xs[s_]))
+        assert np.array_equal(got[s_].view(np.uint32), want.view(np.uint32)), s_
+    assert np.array_equal(b.view(np.uint32), b2.view(np.uint32))
+    f.reset()
+    assert np.array_equal(f.process(np.ascontiguousarray(xs[:, :50])).view(np.uint32), got[:, :50].view(np.uint32))
+
+
 def test_pll_filter_adaptor(sdr):
     """source.filter(PllDesign) (main.rs:49): (value, locked) <-> Option<f32>"""
     S = sdr.signal

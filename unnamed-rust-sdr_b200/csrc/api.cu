@@ -835,6 +835,125 @@ extern "C" int sdr_pll_get_state(sdr_pll_t *p, size_t idx, float *nphase, float 
 }
 
 // ============================================================================================
+// Biquad stream filter
+// ============================================================================================
+struct sdr_biquad {
+    int dev = 0;
+    StreamRef stream;
+    size_t n_streams = 0, n_designs = 0;
+    int W = 1;
+    std::vector<float> coef;  // 5 per design
+    std::vector<int> kind;
+    float *d_coef = nullptr, *d_state = nullptr;
+    int *d_kind = nullptr;
+    DevBuf d_in, d_out;
+};
+static void biquad_free(sdr_biquad *b) {
+    if (!b) return;
+    DeviceGuard g(b->dev);
+    if (b->d_coef) cudaFree(b->d_coef);
+    if (b->d_kind) cudaFree(b->d_kind);
+    if (b->d_state) cudaFree(b->d_state);
+    b->d_in.release(); b->d_out.release();
+    b->stream.release();
+    delete b;
+}
+static int biquad_alloc(sdr_biquad *b, void *user_stream) {
+    int rc = b->stream.init(user_stream);
+    if (rc) return rc;
+    const size_t nseq = b->n_streams * b->W;
+    SDR_CUDA_TRY(cudaMalloc(&b->d_coef, b->coef.size() * sizeof(float)));
+    SDR_CUDA_TRY(cudaMalloc(&b->d_kind, b->kind.size() * sizeof(int)));
+    SDR_CUDA_TRY(cudaMalloc(&b->d_state, nseq * 4 * sizeof(float)));
+    SDR_CUDA_TRY(cudaMemcpyAsync(b->d_coef, b->coef.data(), b->coef.size() * sizeof(float), cudaMemcpyHostToDevice, b->stream.s));
+    SDR_CUDA_TRY(cudaMemcpyAsync(b->d_kind, b->kind.data(), b->kind.size() * sizeof(int), cudaMemcpyHostToDevice, b->stream.s));
+    SDR_CUDA_TRY(cudaMemsetAsync(b->d_state, 0, nseq * 4 * sizeof(float), b->stream.s));
+    return cuda_status(cudaStreamSynchronize(b->stream.s));
+}
+extern "C" sdr_biquad_t *sdr_biquad_create(const sdr_biquad_config_t *cfg, int *err) {
+    int dummy;
+    if (!err) err = &dummy;
+    *err = SDR_OK;
+    if (!cfg || !cfg->designs || cfg->n_streams == 0 || cfg->n_streams > (1u << 24) ||
+        (cfg->n_designs != 1 && cfg->n_designs != cfg->n_streams)) {
+        *err = SDR_ERR_INVALID_ARG;
+        return nullptr;
+    }
+    if ((*err = check_device(cfg->device)) != SDR_OK) return nullptr;
+    sdr_biquad *b = new (std::nothrow) sdr_biquad;
+    if (!b) { *err = SDR_ERR_MALLOC_FAILED; return nullptr; }
+    b->dev = cfg->device;
+    b->n_streams = cfg->n_streams;
+    b->n_designs = cfg->n_designs;
+    b->W = cfg->sample_complex ? 2 : 1;
+    b->coef.resize(5 * cfg->n_designs);
+    b->kind.resize(cfg->n_designs);
+    for (size_t i = 0; i < cfg->n_designs; ++i) {
+        b->kind[i] = cfg->designs[i].kind;
+        const int rc = sdr_biquad_design(&cfg->designs[i], cfg->rate, &b->coef[5 * i]);
+        if (rc) { *err = rc; delete b; return nullptr; }
+    }
+    DeviceGuard g(b->dev);
+    *err = biquad_alloc(b, cfg->stream);
+    if (*err) { biquad_free(b); return nullptr; }
+    return b;
+}
+extern "C" void sdr_biquad_destroy(sdr_biquad_t *b) { biquad_free(b); }
+extern "C" int sdr_biquad_reset(sdr_biquad_t *b) {
+    if (!b) return SDR_ERR_NULL_HANDLE;
+    DeviceGuard g(b->dev);
+    SDR_CUDA_TRY(cudaMemsetAsync(b->d_state, 0, b->n_streams * b->W * 4 * sizeof(float), b->stream.s));
+    return cuda_status(cudaStreamSynchronize(b->stream.s));
+}
+extern "C" sdr_biquad_t *sdr_biquad_clone(const sdr_biquad_t *src, int *err) {
+    int dummy;
+    if (!err) err = &dummy;
+    *err = SDR_OK;
+    if (!src) { *err = SDR_ERR_NULL_HANDLE; return nullptr; }
+    sdr_biquad *b = new (std::nothrow) sdr_biquad;
+    if (!b) { *err = SDR_ERR_MALLOC_FAILED; return nullptr; }
+    b->dev = src->dev; b->n_streams = src->n_streams; b->n_designs = src->n_designs; b->W = src->W;
+    b->coef = src->coef; b->kind = src->kind;
+    DeviceGuard g(b->dev);
+    *err = biquad_alloc(b, src->stream.owned ? nullptr : (void *)src->stream.s);
+    if (!*err) *err = cuda_status(cudaStreamSynchronize(src->stream.s));
+    if (!*err)
+        *err = cuda_status(cudaMemcpy(b->d_state, src->d_state, b->n_streams * b->W * 4 * sizeof(float), cudaMemcpyDeviceToDevice));
+    if (*err) { biquad_free(b); return nullptr; }
+    return b;
+}
+extern "C" int sdr_biquad_process_dev(sdr_biquad_t *b, const float *in, size_t n, size_t in_stride, float *out, size_t out_stride) {
+    if (!b) return SDR_ERR_NULL_HANDLE;
+    if (n == 0) return SDR_OK;
+    if (!in || !out) return SDR_ERR_BAD_DATA_PTR;
+    if (b->n_streams == 1) { in_stride = n; out_stride = n; }
+    if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
+    DeviceGuard g(b->dev);
+    return biquad_launch(in, (long long)n, (long long)in_stride, out, (long long)out_stride, b->W, b->d_coef, b->d_kind,
+                         b->n_designs == 1, b->d_state, (int)(b->n_streams * b->W), b->stream.s);
+}
+extern "C" int sdr_biquad_process(sdr_biquad_t *b, const float *in, size_t n, size_t in_stride, float *out, size_t out_stride) {
+    if (!b) return SDR_ERR_NULL_HANDLE;
+    if (n == 0) return SDR_OK;
+    if (!in || !out) return SDR_ERR_BAD_DATA_PTR;
+    if (b->n_streams == 1) { in_stride = n; out_stride = n; }
+    if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
+    DeviceGuard g(b->dev);
+    const size_t S = b->n_streams, eb = 4 * (size_t)b->W;
+    int rc = b->d_in.reserve(S * n * eb);
+    if (!rc) rc = b->d_out.reserve(S * n * eb);
+    if (rc) return rc;
+    cudaStream_t st = b->stream.s;
+    rc = copy2d(b->d_in.p, n * eb, in, in_stride * eb, n * eb, S, cudaMemcpyHostToDevice, st);
+    if (!rc)
+        rc = biquad_launch((const float *)b->d_in.p, (long long)n, (long long)n, (float *)b->d_out.p, (long long)n, b->W,
+                           b->d_coef, b->d_kind, b->n_designs == 1, b->d_state, (int)(S * b->W), st);
+    if (!rc) rc = copy2d(out, out_stride * eb, b->d_out.p, n * eb, n * eb, S, cudaMemcpyDeviceToHost, st);
+    if (rc) return rc;
+    return cuda_status(cudaStreamSynchronize(st));
+}
+
+// ============================================================================================
 // channelizer: n_channels x (FIR -> PLL).  The FIR output is produced in L2-sized slabs that the
 // PLL kernel consumes immediately on the same stream.
 // ============================================================================================

@@ -89,6 +89,11 @@ int pll_launch(const float2 *in, long long n, long long in_stride, float *out, u
                long long out_stride, const PllParams *params, int params_shared, PllState *state,
                int n_streams, bool fast_math, cudaStream_t st);
 
+// stand-alone biquad stream filter: n_seq real sequences (a complex stream is two), element i of sequence s at
+// in[(s / W) * in_stride * W + i * W + s % W], W = 1 (f32) or 2 (c64); coef / state: 5 / 4 floats per sequence
+int biquad_launch(const float *in, long long n, long long in_stride, float *out, long long out_stride, int W,
+                  const float *coef, const int *kind, int coef_shared, float *state, int n_seq, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------
 // resampler (resample.cu)
 // ---------------------------------------------------------------------------------------

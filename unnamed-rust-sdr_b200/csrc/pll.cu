@@ -255,7 +255,55 @@ __global__ void __launch_bounds__(32) pll_kernel(const float2 *__restrict__ in, 
     if (live) state[my] = st;
 }
 
+// Stand-alone Biquad stream filter (biquad.rs:40-56): one lane per real sequence, [32 sequences x 32 samples]
+// tiles staged through shared memory like the PLL's.  W = 1: f32 streams; W = 2: c64 streams, lanes 2s, 2s+1 = re, im.
+__global__ void __launch_bounds__(32) biquad_kernel(const float *__restrict__ in, long long n, long long in_stride,
+                                                    float *__restrict__ out, long long out_stride, int W,
+                                                    const float *__restrict__ coef, const int *__restrict__ kind,
+                                                    int coef_shared, float *__restrict__ state, int n_seq) {
+    __shared__ float s_x[32][PLL_CHUNK + 1];
+    const int lane = threadIdx.x;
+    const int seq0 = blockIdx.x * 32;
+    if (seq0 >= n_seq) return;
+    const int my = seq0 + lane;
+    const bool live = my < n_seq;
+    const int cs = coef_shared ? 0 : (live ? my / W : seq0 / W);
+    const Biquad1 bq = make_bq(coef + 5 * cs, kind[cs]);
+    float x1 = 0.f, x2 = 0.f, y1 = 0.f, y2 = 0.f;
+    if (live) { x1 = state[4 * my]; x2 = state[4 * my + 1]; y1 = state[4 * my + 2]; y2 = state[4 * my + 3]; }
+    const int nrows = min(32, n_seq - seq0);
+    // row r of the tile = sequence seq0 + r: stream (seq0 + r) / W, part (seq0 + r) % W
+    for (long long base = 0; base < n; base += PLL_CHUNK) {
+        const int cnt = (int)min((long long)PLL_CHUNK, n - base);
+        if (lane < cnt)
+            for (int r = 0; r < nrows; ++r) {
+                const int sq = seq0 + r;
+                s_x[r][lane] = in[((long long)(sq / W) * in_stride + base + lane) * W + sq % W];
+            }
+        __syncwarp();
+        if (live)
+            for (int i = 0; i < cnt; ++i) s_x[lane][i] = bq_apply(bq, s_x[lane][i], x1, x2, y1, y2);
+        __syncwarp();
+        if (lane < cnt)
+            for (int r = 0; r < nrows; ++r) {
+                const int sq = seq0 + r;
+                out[((long long)(sq / W) * out_stride + base + lane) * W + sq % W] = s_x[r][lane];
+            }
+        __syncwarp();
+    }
+    if (live) { state[4 * my] = x1; state[4 * my + 1] = x2; state[4 * my + 2] = y1; state[4 * my + 3] = y2; }
+}
+
 }  // namespace
+
+int biquad_launch(const float *in, long long n, long long in_stride, float *out, long long out_stride, int W,
+                  const float *coef, const int *kind, int coef_shared, float *state, int n_seq, cudaStream_t st) {
+    if (n <= 0 || n_seq <= 0) return SDR_OK;
+    biquad_kernel<<<(unsigned)((n_seq + 31) / 32), 32, 0, st>>>(in, n, in_stride, out, out_stride, W, coef, kind,
+                                                                 coef_shared, state, n_seq);
+    count_launch();
+    return launch_status();
+}
 
 int pll_launch(const float2 *in, long long n, long long in_stride, float *out, uint8_t *locked, long long out_stride,
                const PllParams *params, int params_shared, PllState *state, int n_streams, bool fast_math,

@@ -13,7 +13,7 @@
 //   rtltcp::RtlTcpSignal (rtltcp.rs:151-168)           sdr::signal::from_u8iq(rate, bytes)
 //   filter::Fir<C,A>, FilterDesign for Vec<C>          sdr::filter::Fir<C,A>  (+ block process(), mirroring
 //     (src/filter/fir.rs)                                SampleRate::process, since a per-sample GPU call is absurd)
-//   filter::BiquadD, Identity, PllDesign, Pll          sdr::filter::BiquadD, Identity, PllDesign, Pll
+//   filter::BiquadD, Biquad, Identity, PllDesign, Pll  sdr::filter::BiquadD, Biquad<A>, Identity, PllDesign, Pll
 //   resample::SampleRate<A>, ConverterType, Error      sdr::resample::SampleRate<A>, ConverterType, Error
 //     (src/resample.rs)
 //   fft::fft, fft::rfft (src/fft.rs)                   sdr::fft::fft, sdr::fft::rfft
@@ -184,6 +184,38 @@ struct BiquadD {  // biquad.rs:74-81 + simple.rs Identity
     static BiquadD Notch(float f, float q) { return {{SDR_BQ_NOTCH, f, q}}; }
     static BiquadD Lr(float decayrate) { return {{SDR_BQ_LR, decayrate, 0.0f}}; }
     static BiquadD Identity() { return {{SDR_BQ_IDENTITY, 0.0f, 0.0f}}; }
+};
+
+// Biquad<f32, A> (biquad.rs:5-71) as a block stream filter; BiquadD::design(rate) (biquad.rs:83-154) builds it
+template <class A>
+class Biquad {
+    sdr_biquad_t *h_ = nullptr;
+
+  public:
+    Biquad(const BiquadD &d, float rate) {
+        sdr_biquad_config_t cfg{};
+        cfg.designs = &d.d;
+        cfg.n_designs = 1;
+        cfg.n_streams = 1;
+        cfg.rate = rate;
+        cfg.sample_complex = SampleTraits<A>::channels == 2;
+        int err = 0;
+        h_ = sdr_biquad_create(&cfg, &err);
+        if (!h_) throw sdr::Error(err, "BiquadD::design");
+    }
+    Biquad(Biquad &&o) noexcept : h_(o.h_) { o.h_ = nullptr; }
+    Biquad(const Biquad &o) {
+        int err = 0;
+        h_ = sdr_biquad_clone(o.h_, &err);
+        if (!h_) throw sdr::Error(err, "Biquad::clone");
+    }
+    ~Biquad() { sdr_biquad_destroy(h_); }
+    void process(const A *in, size_t n, std::vector<A> &out) {
+        out.resize(n);
+        check(sdr_biquad_process(h_, reinterpret_cast<const float *>(in), n, n, reinterpret_cast<float *>(out.data()), n),
+              "Biquad::apply");
+    }
+    void reset() { check(sdr_biquad_reset(h_), "Biquad::reset"); }
 };
 
 class Pll;

@@ -19,6 +19,7 @@ pub const SDR_FFT_RFFT: c_uint = 4;
 pub enum sdr_fir_t {}
 pub enum sdr_fft_t {}
 pub enum sdr_pll_t {}
+pub enum sdr_biquad_t {}
 pub enum sdr_channelizer_t {}
 /// same role as libsamplerate's SRC_STATE (src/resample.rs:12)
 pub enum SDR_SRC_STATE {}
@@ -74,6 +75,17 @@ pub struct sdr_pll_config_t {
     pub stream: *mut c_void,
 }
 
+#[repr(C)]
+pub struct sdr_biquad_config_t {
+    pub designs: *const sdr_biquad_design_t,
+    pub n_designs: size_t,
+    pub n_streams: size_t,
+    pub rate: c_float,
+    pub sample_complex: c_int,
+    pub device: c_int,
+    pub stream: *mut c_void,
+}
+
 /// identical layout to libsamplerate's SRC_DATA as built at src/resample.rs:49-58
 #[repr(C)]
 pub struct SDR_SRC_DATA {
@@ -116,6 +128,14 @@ extern "C" {
     pub fn sdr_pll_process(p: *mut sdr_pll_t, in_c64: *const c_float, n: size_t, in_stride: size_t,
                            out: *mut c_float, locked: *mut u8, out_stride: size_t) -> c_int;
     pub fn sdr_pll_get_state(p: *mut sdr_pll_t, idx: size_t, nphase: *mut c_float, re: *mut c_float, im: *mut c_float) -> c_int;
+
+    // Biquad<f32, A> as a stream filter (src/filter/biquad.rs:40-56)
+    pub fn sdr_biquad_create(cfg: *const sdr_biquad_config_t, err: *mut c_int) -> *mut sdr_biquad_t;
+    pub fn sdr_biquad_destroy(b: *mut sdr_biquad_t);
+    pub fn sdr_biquad_reset(b: *mut sdr_biquad_t) -> c_int;
+    pub fn sdr_biquad_clone(b: *const sdr_biquad_t, err: *mut c_int) -> *mut sdr_biquad_t;
+    pub fn sdr_biquad_process(b: *mut sdr_biquad_t, input: *const c_float, n: size_t, in_stride: size_t,
+                              output: *mut c_float, out_stride: size_t) -> c_int;
 
     // drop-in for libsamplerate_sys::{src_new, src_process, ...} used by src/resample.rs
     pub fn sdr_src_new(converter_type: c_int, channels: c_int, error: *mut c_int) -> *mut SDR_SRC_STATE;

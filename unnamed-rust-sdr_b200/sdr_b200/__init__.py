@@ -4,7 +4,7 @@ sample-stream hot path of agrif/unnamed-rust-sdr.  Module layout follows the ref
 the built CUDA library or without a CUDA device raises."""
 from . import _ffi
 from ._ffi import (FMT_C64, FMT_F32, FMT_U8IQ, LIB_PATH, PROTOTYPES, SdrError, lib)
-from .ops import (BiquadD, Channelizer, ConverterType, FftPlan, Fir, Identity, PllBatch, PllDesign,
+from .ops import (Biquad, BiquadD, Channelizer, ConverterType, FftPlan, Fir, Identity, PllBatch, PllDesign,
                   ResampleError, SampleRate, Timer, block_samples, decimate_wait, device_count,
                   device_info, duration_samples, fft, fft_labels, kernel_launch_count, rfft, sinc_table,
                   unpack_u8iq)

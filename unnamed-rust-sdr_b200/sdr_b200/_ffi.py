@@ -39,6 +39,11 @@ class PllConfig(C.Structure):
                 ("flags", C.c_uint), ("device", i32), ("stream", vp)]
 
 
+class BiquadConfig(C.Structure):
+    _fields_ = [("designs", vp), ("n_designs", sz), ("n_streams", sz), ("rate", f32),
+                ("sample_complex", i32), ("device", i32), ("stream", vp)]
+
+
 class SrcData(C.Structure):
     _fields_ = [("data_in", vp), ("data_out", vp), ("input_frames", C.c_long), ("output_frames", C.c_long),
                 ("input_frames_used", C.c_long), ("output_frames_gen", C.c_long),
@@ -78,6 +83,12 @@ PROTOTYPES = {
     "sdr_pll_process": (i32, [vp, vp, sz, sz, vp, vp, sz]),
     "sdr_pll_process_dev": (i32, [vp, vp, sz, sz, vp, vp, sz]),
     "sdr_pll_get_state": (i32, [vp, sz, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32)]),
+    "sdr_biquad_create": (vp, [C.POINTER(BiquadConfig), C.POINTER(i32)]),
+    "sdr_biquad_destroy": (None, [vp]),
+    "sdr_biquad_reset": (i32, [vp]),
+    "sdr_biquad_clone": (vp, [vp, C.POINTER(i32)]),
+    "sdr_biquad_process": (i32, [vp, vp, sz, sz, vp, sz]),
+    "sdr_biquad_process_dev": (i32, [vp, vp, sz, sz, vp, sz]),
     "sdr_channelizer_create": (vp, [C.POINTER(FirConfig), C.POINTER(PllConfig), C.POINTER(i32)]),
     "sdr_channelizer_destroy": (None, [vp]),
     "sdr_channelizer_reset": (i32, [vp]),

@@ -244,6 +244,58 @@ class BiquadD:
 Identity = BiquadD.Identity
 
 
+class Biquad:
+    """filter::Biquad<f32, A> as a stream filter (biquad.rs:40-56): n_streams independent streams of f32 or
+    Complex<f32> samples; designs = one BiquadD shared by all streams, or one per stream."""
+
+    def __init__(self, designs, rate, n_streams=1, complex_samples=False, device=0, stream=None, _handle=None, _meta=None):
+        if _handle is not None:
+            self.h = _handle
+            self.__dict__.update(_meta)
+            return
+        if isinstance(designs, BiquadD):
+            designs = [designs]
+        self.n_streams, self.complex_samples = int(n_streams), bool(complex_samples)
+        arr = (F.BiquadDesign * len(designs))(*[d._c() for d in designs])
+        self._arr = arr
+        cfg = F.BiquadConfig(C.cast(arr, C.c_void_p), len(designs), self.n_streams, rate, int(self.complex_samples),
+                             device, _stream_ptr(stream))
+        err = C.c_int(0)
+        self.h = lib().sdr_biquad_create(C.byref(cfg), C.byref(err))
+        if not self.h:
+            raise SdrError(err.value, "sdr_biquad_create")
+
+    def process(self, x):
+        dt = np.complex64 if self.complex_samples else np.float32
+        x = np.ascontiguousarray(x, dt)
+        rows = x.reshape(self.n_streams, -1)
+        n = rows.shape[1]
+        out = np.empty_like(rows)
+        check(lib().sdr_biquad_process(self.h, rows.ctypes.data, n, n, out.ctypes.data, n), "sdr_biquad_process")
+        return out[0] if x.ndim <= 1 else out
+
+    def process_dev(self, d_in, n, d_out, in_stride=None, out_stride=None):
+        check(lib().sdr_biquad_process_dev(self.h, _ptr(d_in), n, in_stride or n, _ptr(d_out), out_stride or n),
+              "sdr_biquad_process_dev")
+
+    def reset(self):
+        check(lib().sdr_biquad_reset(self.h), "sdr_biquad_reset")
+
+    def clone(self):
+        err = C.c_int(0)
+        h = lib().sdr_biquad_clone(self.h, C.byref(err))
+        if not h:
+            raise SdrError(err.value, "sdr_biquad_clone")
+        return Biquad(None, 0, _handle=h, _meta={k: v for k, v in self.__dict__.items() if k not in ("h", "_arr")})
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sdr_biquad_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
 class PllDesign:
     """filter::PllDesign::new(reference, gain, loopfilter, outputfilter, lockfilter) (pll.rs:26-36)."""
 
