@@ -697,6 +697,7 @@ struct sdr_pll {
     size_t n_streams = 0, n_designs = 0;
     unsigned flags = 0;
     std::vector<PllParams> params;
+    bool any_identity = false;  // some sub-filter is filter::Identity: the kernel keeps its per-filter kind tests
     PllParams *d_params = nullptr;
     PllState *d_state = nullptr;
     DevBuf d_in, d_out, d_lk;
@@ -748,6 +749,7 @@ extern "C" sdr_pll_t *sdr_pll_create(const sdr_pll_config_t *cfg, int *err) {
         q.gain = d.gain;
         q.rate = cfg->rate;
         q.lk = d.loopfilter.kind; q.ok = d.outputfilter.kind; q.kk = d.lockfilter.kind;
+        if (q.lk == SDR_BQ_IDENTITY || q.ok == SDR_BQ_IDENTITY || q.kk == SDR_BQ_IDENTITY) p->any_identity = true;
         int rc = sdr_biquad_design(&d.loopfilter, cfg->rate, q.lc);
         if (!rc) rc = sdr_biquad_design(&d.outputfilter, cfg->rate, q.oc);
         if (!rc) rc = sdr_biquad_design(&d.lockfilter, cfg->rate, q.kc);
@@ -774,6 +776,7 @@ extern "C" sdr_pll_t *sdr_pll_clone(const sdr_pll_t *src, int *err) {
     if (!p) { *err = SDR_ERR_MALLOC_FAILED; return nullptr; }
     p->dev = src->dev; p->n_streams = src->n_streams; p->n_designs = src->n_designs; p->flags = src->flags;
     p->params = src->params;
+    p->any_identity = src->any_identity;
     DeviceGuard g(p->dev);
     *err = pll_alloc(p, src->stream.owned ? nullptr : (void *)src->stream.s);
     if (!*err) *err = cuda_status(cudaStreamSynchronize(src->stream.s));
@@ -792,7 +795,7 @@ extern "C" int sdr_pll_process_dev(sdr_pll_t *p, const float *in, size_t n, size
     DeviceGuard g(p->dev);
     return pll_launch((const float2 *)in, (long long)n, (long long)in_stride, out, locked, (long long)out_stride,
                       p->d_params, p->n_designs == 1, p->d_state, (int)p->n_streams,
-                      (p->flags & SDR_PLL_FAST_MATH) != 0, p->stream.s);
+                      (p->flags & SDR_PLL_FAST_MATH) != 0, p->any_identity, p->stream.s);
 }
 
 extern "C" int sdr_pll_process(sdr_pll_t *p, const float *in, size_t n, size_t in_stride, float *out, uint8_t *locked,
@@ -813,7 +816,7 @@ extern "C" int sdr_pll_process(sdr_pll_t *p, const float *in, size_t n, size_t i
     if (rc) return rc;
     rc = pll_launch((const float2 *)p->d_in.p, (long long)n, (long long)n, (float *)p->d_out.p, (uint8_t *)p->d_lk.p,
                     (long long)n, p->d_params, p->n_designs == 1, p->d_state, (int)S,
-                    (p->flags & SDR_PLL_FAST_MATH) != 0, st);
+                    (p->flags & SDR_PLL_FAST_MATH) != 0, p->any_identity, st);
     if (rc) return rc;
     rc = copy2d(out, out_stride * 4, p->d_out.p, n * 4, n * 4, S, cudaMemcpyDeviceToHost, st);
     if (!rc) rc = copy2d(locked, out_stride, p->d_lk.p, n, n, S, cudaMemcpyDeviceToHost, st);

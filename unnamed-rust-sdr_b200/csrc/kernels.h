@@ -87,7 +87,7 @@ struct PllState {       // per stream, device resident
 };
 int pll_launch(const float2 *in, long long n, long long in_stride, float *out, uint8_t *locked,
                long long out_stride, const PllParams *params, int params_shared, PllState *state,
-               int n_streams, bool fast_math, cudaStream_t st);
+               int n_streams, bool fast_math, bool any_identity, cudaStream_t st);
 
 // stand-alone biquad stream filter: n_seq real sequences (a complex stream is two), element i of sequence s at
 // in[(s / W) * in_stride * W + i * W + s % W], W = 1 (f32) or 2 (c64); coef / state: 5 / 4 floats per sequence

@@ -26,8 +26,10 @@ struct Biquad1 {
     int kind;
 };
 
+// GEN = false: the caller knows the filter is not filter::Identity (no kind test on the dependent chain)
+template <bool GEN = true>
 __device__ __forceinline__ float bq_apply(const Biquad1 &c, float v, float &x1, float &x2, float &y1, float &y2) {
-    if (c.kind == SDR_BQ_IDENTITY) return v;
+    if (GEN && c.kind == SDR_BQ_IDENTITY) return v;
     // out = 0; out += v*b0; out += x1*b1; out += x2*b2; out += y1*na1; out += y2*na2  (biquad.rs:44-49)
     float out = __fadd_rn(0.0f, __fmul_rn(v, c.b0));
     out = __fadd_rn(out, __fmul_rn(x1, c.b1));
@@ -47,19 +49,18 @@ template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
 template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
 
-// num / den for finite den != 0: f32 reciprocal seed + Newton steps in T (error ~2^-46 in double, ~1 ulp in float)
-__device__ __forceinline__ double div_t(double num, double den) {
-    const float df = (float)den;
-    if (!(fabsf(df) > 1e-30f && fabsf(df) < 1e30f)) return num / den;  // outside the f32 seed's comfortable range
-    double r = (double)__frcp_rn(df);
-    r = fma_t(r, fma_t(-den, r, 1.0), r);
-    const double q = num * r;
-    return fma_t(fma_t(-den, q, num), r, q);
-}
-__device__ __forceinline__ float div_t(float num, float den) {
-    if (!(fabsf(den) > 1e-30f && fabsf(den) < 1e30f)) return num / den;
-    const float r = __frcp_rn(den);
-    const float q = num * r;
+// num / den for finite den != 0, |num| <= |den| up to a factor 2: f32 reciprocal seed + Newton steps in T (error ~2^-46
+// in double, ~1 ulp in float).  Branch-free: operands far from 1 are first rescaled by 2^+-64 (exact) so that the seed
+// neither overflows nor flushes -- a NaN here would poison the loop state for good.
+template <typename T>
+__device__ __forceinline__ T div_t(T num, T den) {
+    const float ad = fabsf((float)den);
+    const T sc = ad < 5.4210109e-20f ? T(1.8446744073709552e19) : (ad > 1.8446744e19f ? T(5.421010862427522e-20) : T(1.0));
+    num *= sc;
+    den *= sc;
+    T r = (T)__frcp_rn((float)den);
+    if (sizeof(T) == 8) r = fma_t(r, fma_t(-den, r, T(1.0)), r);
+    const T q = num * r;
     return fma_t(fma_t(-den, q, num), r, q);
 }
 
@@ -134,7 +135,7 @@ __device__ __forceinline__ void sincos_t(float xf, T &sn, T &cs) {
     cs = ((q + 1) & 2) ? -b : b;
 }
 
-template <bool FAST>
+template <bool FAST, bool GEN>
 __device__ __forceinline__ void pll_step(const PllParams &p, const Biquad1 &lf, const Biquad1 &of, const Biquad1 &kf,
                                          PllState &s, float xr, float xi, float &out, uint8_t &locked) {
     // c = value * self.value.conj()           (pll.rs:71)   other = (vre, -vim)
@@ -142,8 +143,8 @@ __device__ __forceinline__ void pll_step(const PllParams &p, const Biquad1 &lf, 
     const float cr = __fsub_rn(__fmul_rn(xr, o_re), __fmul_rn(xi, o_im));
     const float ci = __fadd_rn(__fmul_rn(xr, o_im), __fmul_rn(xi, o_re));
     // loopfilter.apply(c): Biquad<f32, Complex<f32>> acts on re and im independently
-    const float lr = bq_apply(lf, cr, s.lx1r, s.lx2r, s.ly1r, s.ly2r);
-    const float li = bq_apply(lf, ci, s.lx1i, s.lx2i, s.ly1i, s.ly2i);
+    const float lr = bq_apply<GEN>(lf, cr, s.lx1r, s.lx2r, s.ly1r, s.ly2r);
+    const float li = bq_apply<GEN>(lf, ci, s.lx1i, s.lx2i, s.ly1i, s.ly2i);
     // phasedif = arg * gain                   (pll.rs:72)
     const float arg = FAST ? atan2_t<float>(li, lr) : (float)atan2_t<double>(li, lr);
     const float phasedif = __fmul_rn(arg, p.gain);
@@ -165,8 +166,8 @@ __device__ __forceinline__ void pll_step(const PllParams &p, const Biquad1 &lf, 
         s.vim = (float)sn;
     }
     // locked = lockfilter.apply(c.re); output = outputfilter.apply(phasedif * rate)   (pll.rs:78-79)
-    const float lk = bq_apply(kf, cr, s.kx1, s.kx2, s.ky1, s.ky2);
-    out = bq_apply(of, __fmul_rn(phasedif, p.rate), s.ox1, s.ox2, s.oy1, s.oy2);
+    const float lk = bq_apply<GEN>(kf, cr, s.kx1, s.kx2, s.ky1, s.ky2);
+    out = bq_apply<GEN>(of, __fmul_rn(phasedif, p.rate), s.ox1, s.ox2, s.oy1, s.oy2);
     locked = lk > 0.01f ? 1 : 0;
 }
 
@@ -187,7 +188,7 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 // One warp (= one CTA) owns 32 streams.  [32 streams x 32 samples] tiles are staged through shared memory: the
 // next tile streams in with cp.async (256-byte row segments) while the lanes step the current one, so the
 // sequential per-stream loop never waits on HBM; outputs leave as 128-byte row segments.
-template <bool FAST>
+template <bool FAST, bool GEN>
 __global__ void __launch_bounds__(32) pll_kernel(const float2 *__restrict__ in, long long n, long long in_stride,
                                                  float *__restrict__ out, uint8_t *__restrict__ locked,
                                                  long long out_stride, const PllParams *__restrict__ params,
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(32) pll_kernel(const float2 *__restrict__ in, 
                 xn = s_in[buf][lane][min(i + 1, PLL_CHUNK - 1)];  // next sample's load leaves the dependent chain
                 float o;
                 uint8_t l;
-                pll_step<FAST>(p, lf, of, kf, st, x.x, x.y, o, l);
+                pll_step<FAST, GEN>(p, lf, of, kf, st, x.x, x.y, o, l);
                 s_out[lane][i] = o;
                 s_lk[lane][i] = l;
             }
@@ -307,13 +308,12 @@ int biquad_launch(const float *in, long long n, long long in_stride, float *out,
 
 int pll_launch(const float2 *in, long long n, long long in_stride, float *out, uint8_t *locked, long long out_stride,
                const PllParams *params, int params_shared, PllState *state, int n_streams, bool fast_math,
-               cudaStream_t st) {
+               bool any_identity, cudaStream_t st) {
     if (n <= 0 || n_streams <= 0) return SDR_OK;
     const unsigned grid = (unsigned)((n_streams + 31) / 32);
-    if (fast_math)
-        pll_kernel<true><<<grid, 32, 0, st>>>(in, n, in_stride, out, locked, out_stride, params, params_shared, state, n_streams);
-    else
-        pll_kernel<false><<<grid, 32, 0, st>>>(in, n, in_stride, out, locked, out_stride, params, params_shared, state, n_streams);
+    auto go = [&](auto kern) { kern<<<grid, 32, 0, st>>>(in, n, in_stride, out, locked, out_stride, params, params_shared, state, n_streams); };
+    if (fast_math) { if (any_identity) go(pll_kernel<true, true>); else go(pll_kernel<true, false>); }
+    else { if (any_identity) go(pll_kernel<false, true>); else go(pll_kernel<false, false>); }
     count_launch();
     return launch_status();
 }
