@@ -70,13 +70,6 @@ struct TcArgs {
     int ntiles;         // tiles per channel
 };
 
-__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem_src));
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::); }
-
 // 16-byte chunk swizzle of the fp16 planes: rows of an ldmatrix 8x8 block are 2*D chunks apart (P = 16), which for
 // D = 1 would put rows r and r+4 on the same bank group; XOR-ing bit 3 into bit 0 separates them.
 __device__ __forceinline__ int swz(int chunk) { return chunk ^ ((chunk >> 3) & 1); }
@@ -261,15 +254,10 @@ __global__ void __launch_bounds__(NW * 32, (NW * 32 <= 128) ? 4 : 2) fir_mma_ker
 }
 
 inline unsigned short half_bits_rn(float v) {
-    const __half h = __float2half_rn(v);
-    unsigned short b;
-    std::memcpy(&b, &h, 2);
-    return b;
+    return __half_as_ushort(__float2half_rn(v));
 }
 inline float half_to_float(unsigned short b) {
-    __half h;
-    std::memcpy(&h, &b, 2);
-    return __half2float(h);
+    return __half2float(__ushort_as_half(b));
 }
 
 }  // namespace
