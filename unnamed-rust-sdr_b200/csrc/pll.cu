@@ -135,9 +135,10 @@ __device__ __forceinline__ void sincos_t(float xf, T &sn, T &cs) {
     cs = ((q + 1) & 2) ? -b : b;
 }
 
+// The recurrence (pll.rs:71-76): everything the NEXT sample depends on.  Returns c.re and phasedif for the two filters
+// that do not feed back (lock, output), which a helper warp applies one tile later.
 template <bool FAST, bool GEN>
-__device__ __forceinline__ void pll_step(const PllParams &p, const Biquad1 &lf, const Biquad1 &of, const Biquad1 &kf,
-                                         PllState &s, float xr, float xi, float &out, uint8_t &locked) {
+__device__ __forceinline__ float2 pll_step(const PllParams &p, const Biquad1 &lf, PllState &s, float xr, float xi) {
     // c = value * self.value.conj()           (pll.rs:71)   other = (vre, -vim)
     const float o_re = s.vre, o_im = -s.vim;
     const float cr = __fsub_rn(__fmul_rn(xr, o_re), __fmul_rn(xi, o_im));
@@ -165,10 +166,7 @@ __device__ __forceinline__ void pll_step(const PllParams &p, const Biquad1 &lf, 
         s.vre = (float)cs;
         s.vim = (float)sn;
     }
-    // locked = lockfilter.apply(c.re); output = outputfilter.apply(phasedif * rate)   (pll.rs:78-79)
-    const float lk = bq_apply<GEN>(kf, cr, s.kx1, s.kx2, s.ky1, s.ky2);
-    out = bq_apply<GEN>(of, __fmul_rn(phasedif, p.rate), s.ox1, s.ox2, s.oy1, s.oy2);
-    locked = lk > 0.01f ? 1 : 0;
+    return make_float2(cr, phasedif);
 }
 
 __device__ __forceinline__ Biquad1 make_bq(const float *c, int kind) {
@@ -185,18 +183,22 @@ __device__ __forceinline__ void cp_async8(void *smem_dst, const void *gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// One warp (= one CTA) owns 32 streams.  [32 streams x 32 samples] tiles are staged through shared memory: the
-// next tile streams in with cp.async (256-byte row segments) while the lanes step the current one, so the
-// sequential per-stream loop never waits on HBM; outputs leave as 128-byte row segments.
+// A CTA of two warps owns 32 streams, one lane of each warp per stream.
+//   warp 0 (main)   steps the recurrence, nothing else: per sample one shared load (prefetched) and one shared store
+//   warp 1 (helper) cp.asyncs the next [32 streams x 32 samples] input tile (256-byte row segments), and for the
+//                   PREVIOUS tile applies the two filters that do not feed back -- locked = lockfilter(c.re),
+//                   output = outputfilter(phasedif * rate) (pll.rs:78-84) -- and writes the 128-byte output rows
+// so the ~45 instructions per sample that are not on the dependent chain never delay it.  One barrier per tile.
 template <bool FAST, bool GEN>
-__global__ void __launch_bounds__(32) pll_kernel(const float2 *__restrict__ in, long long n, long long in_stride,
+__global__ void __launch_bounds__(64) pll_kernel(const float2 *__restrict__ in, long long n, long long in_stride,
                                                  float *__restrict__ out, uint8_t *__restrict__ locked,
                                                  long long out_stride, const PllParams *__restrict__ params,
                                                  int params_shared, PllState *__restrict__ state, int n_streams) {
     __shared__ float2 s_in[2][32][PLL_CHUNK + 1];
+    __shared__ float2 s_mid[2][32][PLL_CHUNK + 1];  // (c.re, phasedif) per sample
     __shared__ float s_out[32][PLL_CHUNK + 1];
     __shared__ uint8_t s_lk[32][PLL_CHUNK + 4];
-    const int lane = threadIdx.x;
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
     const int stream0 = blockIdx.x * 32;
     if (stream0 >= n_streams) return;
     const int my = stream0 + lane;
@@ -218,42 +220,64 @@ __global__ void __launch_bounds__(32) pll_kernel(const float2 *__restrict__ in, 
         cp_async_commit();
     };
 
-    issue(0, 0);
-    for (long long tile = 0; tile < ntiles; ++tile) {
+    if (role == 1) {
+        issue(0, 0);
+        cp_async_wait<0>();
+    }
+    __syncthreads();
+    // iteration t: main steps tile t; helper loads tile t+1 and finishes tile t-1
+    for (long long tile = 0; tile <= ntiles; ++tile) {
         const int buf = (int)(tile & 1);
-        const long long base = tile * PLL_CHUNK;
-        const int cnt = (int)min((long long)PLL_CHUNK, n - base);
-        if (tile + 1 < ntiles) {
-            issue(tile + 1, buf ^ 1);
-            cp_async_wait<1>();
+        if (role == 0) {
+            if (tile < ntiles && live) {
+                const int cnt = (int)min((long long)PLL_CHUNK, n - tile * PLL_CHUNK);
+                float2 xn = s_in[buf][lane][0];
+                for (int i = 0; i < cnt; ++i) {
+                    const float2 x = xn;
+                    xn = s_in[buf][lane][min(i + 1, PLL_CHUNK - 1)];  // next sample's load leaves the dependent chain
+                    s_mid[buf][lane][i] = pll_step<FAST, GEN>(p, lf, st, x.x, x.y);
+                }
+            }
         } else {
+            if (tile + 1 < ntiles) issue(tile + 1, buf ^ 1);
+            if (tile > 0) {
+                const long long base = (tile - 1) * PLL_CHUNK;
+                const int cnt = (int)min((long long)PLL_CHUNK, n - base);
+                if (live) {
+                    for (int i = 0; i < cnt; ++i) {
+                        const float2 m = s_mid[buf ^ 1][lane][i];
+                        const float lk = bq_apply<GEN>(kf, m.x, st.kx1, st.kx2, st.ky1, st.ky2);
+                        s_out[lane][i] = bq_apply<GEN>(of, __fmul_rn(m.y, p.rate), st.ox1, st.ox2, st.oy1, st.oy2);
+                        s_lk[lane][i] = lk > 0.01f ? 1 : 0;
+                    }
+                }
+                __syncwarp();
+                if (lane < cnt) {
+#pragma unroll 8
+                    for (int r = 0; r < 32; ++r)
+                        if (r < nrows) {
+                            out[(long long)(stream0 + r) * out_stride + base + lane] = s_out[r][lane];
+                            locked[(long long)(stream0 + r) * out_stride + base + lane] = s_lk[r][lane];
+                        }
+                }
+                __syncwarp();
+            }
             cp_async_wait<0>();
         }
-        __syncwarp();
-        if (live) {
-            float2 xn = s_in[buf][lane][0];
-            for (int i = 0; i < cnt; ++i) {
-                const float2 x = xn;
-                xn = s_in[buf][lane][min(i + 1, PLL_CHUNK - 1)];  // next sample's load leaves the dependent chain
-                float o;
-                uint8_t l;
-                pll_step<FAST, GEN>(p, lf, of, kf, st, x.x, x.y, o, l);
-                s_out[lane][i] = o;
-                s_lk[lane][i] = l;
-            }
-        }
-        __syncwarp();
-        if (lane < cnt) {
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r)
-                if (r < nrows) {
-                    out[(long long)(stream0 + r) * out_stride + base + lane] = s_out[r][lane];
-                    locked[(long long)(stream0 + r) * out_stride + base + lane] = s_lk[r][lane];
-                }
-        }
-        __syncwarp();
+        __syncthreads();
     }
-    if (live) state[my] = st;
+    if (live) {
+        // the two warps hold disjoint parts of the carried state
+        PllState *dst = state + my;
+        if (role == 0) {
+            dst->nphase = st.nphase; dst->vre = st.vre; dst->vim = st.vim;
+            dst->lx1r = st.lx1r; dst->lx1i = st.lx1i; dst->lx2r = st.lx2r; dst->lx2i = st.lx2i;
+            dst->ly1r = st.ly1r; dst->ly1i = st.ly1i; dst->ly2r = st.ly2r; dst->ly2i = st.ly2i;
+        } else {
+            dst->ox1 = st.ox1; dst->ox2 = st.ox2; dst->oy1 = st.oy1; dst->oy2 = st.oy2;
+            dst->kx1 = st.kx1; dst->kx2 = st.kx2; dst->ky1 = st.ky1; dst->ky2 = st.ky2;
+        }
+    }
 }
 
 // Stand-alone Biquad stream filter (biquad.rs:40-56): one lane per real sequence, [32 sequences x 32 samples]
@@ -311,7 +335,7 @@ int pll_launch(const float2 *in, long long n, long long in_stride, float *out, u
                bool any_identity, cudaStream_t st) {
     if (n <= 0 || n_streams <= 0) return SDR_OK;
     const unsigned grid = (unsigned)((n_streams + 31) / 32);
-    auto go = [&](auto kern) { kern<<<grid, 32, 0, st>>>(in, n, in_stride, out, locked, out_stride, params, params_shared, state, n_streams); };
+    auto go = [&](auto kern) { kern<<<grid, 64, 0, st>>>(in, n, in_stride, out, locked, out_stride, params, params_shared, state, n_streams); };
     if (fast_math) { if (any_identity) go(pll_kernel<true, true>); else go(pll_kernel<true, false>); }
     else { if (any_identity) go(pll_kernel<false, true>); else go(pll_kernel<false, false>); }
     count_launch();
