@@ -154,7 +154,7 @@ def test_tensor_path_shapes(sdr, K, D, tc):
         assert len(got) == n // D and rel_err(got, truth) < TOL
 
 
-@pytest.mark.parametrize("D", [2, 3, 4, 5, 6, 7, 10, 12, 20, 50, 8, 16, 96])
+@pytest.mark.parametrize("D", [2, 3, 4, 5, 6, 7, 9, 10, 12, 20, 50, 8, 16, 96])
 @pytest.mark.parametrize("K,tc", [(64, True), (255, False)])
 def test_tcgen05_decimating_path(sdr, D, K, tc):
     """Decimate fused behind the filter on the tensor cores: rows stay 32 samples apart, only the offsets a kept
@@ -169,12 +169,13 @@ def test_tcgen05_decimating_path(sdr, D, K, tc):
     truth = O.fir_f64(taps, O.unpack_u8iq(iq))[D - 1::D]
     f = sdr.Fir(taps, "u8iq", decimation=D)
     whole = f.process(iq)
-    if math.gcd(D, 32) <= 4 and not (D % 2 == 1 and K > 160):
+    poly = D in (5, 6, 7, 8, 9, 10, 12)  # phase-plane kernel: every computed output is kept
+    if poly or (math.gcd(D, 32) <= 4 and not (D % 2 == 1 and K > 160)):
         assert f.last_path == 4
     elif math.gcd(D, 32) <= 4:
         assert f.last_path in (3, 4)  # odd D needs all 32 candidates: 255 taps' tables leave no room for the stages
     else:
-        assert f.last_path in (1, 3)  # D = 8, 16, 96: too few candidates per row for the tcgen05 path
+        assert f.last_path in (1, 3)  # D = 16, 96: too few candidates per row for the tcgen05 path
     assert len(whole) == n // D and rel_err(whole, truth) < (1e-6 if f.last_path == 4 else TOL)
     if f.last_path != 4:
         return

@@ -239,7 +239,7 @@ static int fir_alloc(sdr_fir *f, void *user_stream) {
     if (f->fmt == SDR_FMT_U8IQ && !(f->flags & (SDR_FIR_STRICT_ORDER | SDR_FIR_NO_TENSOR | SDR_FIR_NO_TCGEN05)) && f->D <= (1u << 20) &&
         fir_umma_geometry((int)f->K, (int)f->D, f->taps_complex != 0, (f->flags & SDR_FIR_PLANAR) != 0, &R, &PC, &planar)) {
         std::vector<uint8_t> tab;
-        if (fir_umma_build_tables(f->taps.data(), (int)f->K, f->taps_complex != 0, R, PC, planar != 0, tab, f->um_magic, f->um_sc)) {
+        if (fir_umma_build_tables(f->taps.data(), (int)f->K, f->taps_complex != 0, R, PC, planar, (int)f->D, tab, f->um_magic, f->um_sc)) {
             f->um_R = R;
             f->um_PC = PC;
             f->um_planar = planar;
@@ -339,7 +339,7 @@ static int fir_run_dev(sdr_fir *f, const void *in, size_t n_in, size_t in_stride
     const bool strict = (f->flags & SDR_FIR_STRICT_ORDER) != 0;
     int rc = SDR_ERR_UNSUPPORTED;
     if (f->d_um_tables) {
-        rc = fir_umma_launch(a, f->um_R, f->um_PC, f->um_planar != 0, f->d_um_tables, f->um_magic, f->um_sc, f->stream.s);
+        rc = fir_umma_launch(a, f->um_R, f->um_PC, f->um_planar, f->d_um_tables, f->um_magic, f->um_sc, f->stream.s);
         if (rc == SDR_OK) f->last_path = 4;
     }
     if (rc == SDR_ERR_UNSUPPORTED && f->d_tc_tables) {

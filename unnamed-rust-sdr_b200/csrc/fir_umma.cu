@@ -95,17 +95,28 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
-                 ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+// D[tmem] (+)= A[smem desc] * B[smem desc], u8 x s8 -> s32; the accumulate flag is fixed at compile time (no setp on
+// the issuing thread's critical path)
+template <bool ACC>
+__device__ __forceinline__ void umma_i8c(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n .reg .pred p;\n setp.eq.u32 p, 1, 1;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n .reg .pred p;\n setp.eq.u32 p, 1, 0;\n tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
+                     ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc) : "memory");
 }
-// 16 lanes x 256 bits, twice: thread t gets, for column groups cg = 0, 1 (8 columns each), the column pair
-// 8 cg + 2 (t%4), +1 of lane t/4 (regs 4cg, 4cg+1) and of lane t/4 + 8 (regs 4cg+2, 4cg+3) -- the mma accumulator
-// fragment layout: 4 consecutive threads hold 4 consecutive (I, Q) column pairs of one row = 32 contiguous output bytes
 __device__ __forceinline__ void tmem_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                  : "r"(taddr) : "memory");
+}
+// one lane of a converged warp (elect.sync): unlike `lane == 0`, ptxas KNOWS a single thread follows the branch, so the
+// tcgen05.mma operands stay in uniform registers and no per-instruction election loop is emitted around them
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
@@ -241,14 +252,19 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
             mbar_wait(full_bar(stage), ph);
             mbar_wait(acce_bar(as), aph ^ 1u);
             tc_fence_after();
-            if (lane == 0) {
-                const uint64_t adesc0 = smem_desc(stage0 + (uint32_t)stage * SB, 16, 8 * ROWB, UmLayout<P>::type);
+            if (elect_one()) {
+                // running descriptors: the issuing thread's uniform-datapath work per MMA is two 64-bit adds of
+                // constants (recomputing them from kk cost ~130 cycles per MMA: the real limit of MMA-heavy tiles)
+                uint64_t ad = smem_desc(stage0 + (uint32_t)stage * SB, 16, 8 * ROWB, UmLayout<P>::type);
+                uint64_t bd = bdesc0;
                 const uint32_t d0 = tmem + (uint32_t)(as * UM_ACC_COLS);
-                for (int kk = 0; kk < KS; ++kk) {
-                    const uint64_t bd = bdesc0 + (uint64_t)((kk * N * 32) >> 4);
 #pragma unroll
-                    for (int mb = 0; mb < MB; ++mb)
-                        umma_i8(d0 + mb * N, adesc0 + (uint64_t)((mb * 128 * ROWB + kk * 32) >> 4), bd, idesc, kk > 0);
+                for (int mb = 0; mb < MB; ++mb) umma_i8c<false>(d0 + mb * N, ad + (uint64_t)((mb * 128 * ROWB) >> 4), bd, idesc);
+                for (int kk = 1; kk < KS; ++kk) {
+                    ad += 2;               // 32 bytes along the window
+                    bd += (N * 32) >> 4;   // next tap block
+#pragma unroll
+                    for (int mb = 0; mb < MB; ++mb) umma_i8c<true>(d0 + mb * N, ad + (uint64_t)((mb * 128 * ROWB) >> 4), bd, idesc);
                 }
                 umma_commit(empty_bar(stage));  // the stage may be refilled once these MMAs have read it
                 umma_commit(accf_bar(as));      // ... and the accumulator set is complete
@@ -518,17 +534,23 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_planar_kernel(const Um
             mbar_wait(full_bar(stage), ph);
             mbar_wait(acce_bar(as), aph ^ 1u);
             tc_fence_after();
-            if (lane == 0) {
-                const uint64_t aI = smem_desc(stage0 + (uint32_t)stage * SB, 16, 8 * R, PitchLayout<R>::type);
-                const uint64_t aQ = smem_desc(stage0 + (uint32_t)stage * SB + PB, 16, 8 * R, PitchLayout<R>::type);
+            if (elect_one()) {
+                uint64_t aI = smem_desc(stage0 + (uint32_t)stage * SB, 16, 8 * R, PitchLayout<R>::type);
+                uint64_t aQ = smem_desc(stage0 + (uint32_t)stage * SB + PB, 16, 8 * R, PitchLayout<R>::type);
+                uint64_t bd = bdesc0;
                 const uint32_t d0 = tmem + (uint32_t)(as * UM_ACC_COLS);
-                for (int kk = 0; kk < KS; ++kk) {
-                    const uint64_t bd = bdesc0 + (uint64_t)((kk * N * 32) >> 4);
+#pragma unroll
+                for (int mb = 0; mb < MB; ++mb) {
+                    umma_i8c<false>(d0 + mb * 2 * N, aI + (uint64_t)((mb * 128 * R) >> 4), bd, idesc);
+                    umma_i8c<false>(d0 + mb * 2 * N + N, aQ + (uint64_t)((mb * 128 * R) >> 4), bd, idesc);
+                }
+                for (int kk = 1; kk < KS; ++kk) {
+                    aI += 2; aQ += 2;
+                    bd += (N * 32) >> 4;
 #pragma unroll
                     for (int mb = 0; mb < MB; ++mb) {
-                        const uint64_t ao = (uint64_t)((mb * 128 * R + kk * 32) >> 4);
-                        umma_i8(d0 + mb * 2 * N, aI + ao, bd, idesc, kk > 0);
-                        umma_i8(d0 + mb * 2 * N + N, aQ + ao, bd, idesc, kk > 0);
+                        umma_i8c<true>(d0 + mb * 2 * N, aI + (uint64_t)((mb * 128 * R) >> 4), bd, idesc);
+                        umma_i8c<true>(d0 + mb * 2 * N + N, aQ + (uint64_t)((mb * 128 * R) >> 4), bd, idesc);
                     }
                 }
                 umma_commit(empty_bar(stage));
@@ -677,6 +699,240 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_planar_kernel(const Um
     }
 }
 
+// =====================================================================================================================
+// Polyphase variant for Decimate with D >= 5 (config C3: 255 taps, D = 10).  The candidate-offset kernel above spends
+// its MMAs on all 32/g offsets of a row although only one in D/g is a kept output.  Here the producers split the stream
+// into D PHASE PLANES x_p[n] = x[A0 + D n + p] (a lane takes 8 n x D phases = D raw 16-byte chunks and emits one
+// 16-byte chunk per plane: one PRMT per output word), and
+//     y[m] = sum_p sum_t h_p[t] x_p[m + t],      h_p[t] = c[K-1 - (D t + p - delta)]
+// is D short unit-stride FIRs: per phase a Toeplitz MMA chain with rows 8 outputs apart (16-byte pitch, no swizzle,
+// N = 48), all accumulating into the same TMEM columns, and EVERY computed output is kept.  MMA operand traffic per
+// input sample drops from 33 to 16 bytes, the kept-output test disappears from the epilogue.
+// =====================================================================================================================
+constexpr int UP_TILE_OUT = 1024;  // outputs per tile = 128 rows x 8
+constexpr int UP_SETS = 4;         // accumulator sets of 48 TMEM columns
+constexpr int UP_RAW = 3;          // raw ring slots: cp.async runs 2 tiles ahead (deeper rings measured no better)
+__host__ __device__ constexpr int up_ksteps(int K, int D) { return (7 + (K + 6) / D) / 16 + 1; }
+__host__ __device__ constexpr int up_nsub(int KS) { return 8 * 128 + 16 * KS; }  // sub-samples per plane per tile
+__host__ __device__ constexpr size_t up_smem_bytes(int D, int KS, int stages) {
+    // stages of D planes + tables + raw ring (UP_RAW slots, same size as a stage) + 1 KB slack + barriers
+    return (size_t)(stages + UP_RAW) * D * 2 * up_nsub(KS) + (size_t)D * KS * 48 * 32 + 1024 + 256;
+}
+
+// roles: 8 producer warps (the phase split is the heavy part here), 1 MMA warp, 8 epilogue warps (a tile has one piece)
+constexpr int UP_PROD_WARPS = 8, UP_MMA_WARP = UP_PROD_WARPS, UP_EPI_WARP0 = UP_PROD_WARPS + 1, UP_THREADS = (UP_PROD_WARPS + 1 + 8) * 32;
+
+template <int D>
+__global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmArgs a) {
+    constexpr int N = 48;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * UM_STAGES + 2 * UP_SETS];
+    __shared__ uint32_t tmem_base_s;
+    const FirArgs &f = a.f;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int KS = a.KS, NST = a.stages;
+    const int NSUB = up_nsub(KS), PLB = 2 * NSUB, SB = D * PLB;  // plane / stage bytes
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t stage0 = base;
+    const uint32_t tab_s = stage0 + NST * SB;
+    uint8_t *gen = smem_raw + (base - smem_u32(smem_raw));
+    uint8_t *raw0 = gen + (size_t)NST * SB + (size_t)D * KS * N * 32;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (UM_STAGES + s); };
+    auto accf_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + s); };
+    auto acce_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + UP_SETS + s); };
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.tab);
+        uint4 *dst = reinterpret_cast<uint4 *>(gen + NST * SB);
+        for (int i = tid; i < D * KS * N * 2; i += UP_THREADS) dst[i] = __ldg(src + i);
+    }
+    if (tid == 0) {
+        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full_bar(s), 32 * UP_PROD_WARPS); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < UP_SETS; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 4); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == UP_MMA_WARP) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    const long long nwork = (long long)a.ntiles * f.n_ch;
+    const long long wstride = gridDim.x;
+
+    if (warp < UP_PROD_WARPS) {
+        // ================= producers: raw ring (cp.async, two tiles ahead) -> D phase planes =================
+        const int ptid = warp * 32 + lane;
+        const int nunits = NSUB / 8;  // a unit = 8 sub-samples of every phase = D raw chunks = D plane chunks
+        const int RAWB = SB;
+        auto issue = [&](long long w, int slot) {
+            if (w < nwork) {
+                const int ch = (int)(w / a.ntiles);
+                // first raw sample of the tile; A0 = first - (K-1) - delta is a multiple of 8
+                const long long w0 = f.first - (f.K - 1) - a.delta + (w % a.ntiles) * (long long)(UP_TILE_OUT * D);
+                const unsigned char *in = (const unsigned char *)f.in + (long long)ch * f.in_stride * 2;
+                const unsigned char *hist = (const unsigned char *)f.hist + (long long)ch * f.hist_stride * 2;
+                uint8_t *rs = raw0 + (size_t)slot * RAWB;
+                const uint32_t rs_s = smem_u32(rs);
+                const bool interior = w0 >= 0 && w0 + 8LL * nunits * D <= f.n_in;
+                for (int v = ptid; v < nunits; v += 32 * UP_PROD_WARPS) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) {
+                        const int q = v * D + c;
+                        const long long s0 = w0 + 8LL * q;
+                        if (interior || (s0 >= 0 && s0 + 8 <= f.n_in)) {
+                            cp_async16_s(rs_s + 16u * q, in + 2 * s0);
+                        } else if (s0 < f.n_in) {
+                            unsigned short h[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const long long s = s0 + i;
+                                unsigned short x = 0x8080;
+                                if (s >= 0) { if (s < f.n_in) x = *reinterpret_cast<const unsigned short *>(in + 2 * s); }
+                                else if (s >= -(long long)f.HL) x = *reinterpret_cast<const unsigned short *>(hist + 2 * ((long long)f.HL + s));
+                                h[i] = x;
+                            }
+                            uint4 qv;
+                            qv.x = h[0] | ((unsigned)h[1] << 16); qv.y = h[2] | ((unsigned)h[3] << 16);
+                            qv.z = h[4] | ((unsigned)h[5] << 16); qv.w = h[6] | ((unsigned)h[7] << 16);
+                            *reinterpret_cast<uint4 *>(rs + 16 * q) = qv;  // read back by this same lane
+                        }
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+#pragma unroll
+        for (int i = 0; i < UP_RAW - 1; ++i) issue(blockIdx.x + i * wstride, i);
+        int stage = 0, slot = 0;
+        uint32_t ph = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride) {
+            int s2 = slot + UP_RAW - 1;
+            if (s2 >= UP_RAW) s2 -= UP_RAW;
+            issue(w + (UP_RAW - 1) * wstride, s2);
+            asm volatile("cp.async.wait_group %0;" ::"n"(UP_RAW - 1) : "memory");  // this lane's chunks of tile w have landed
+            mbar_wait(empty_bar(stage), ph ^ 1u);
+            uint8_t *st_g = gen + (size_t)stage * SB;
+            const uint8_t *rs = raw0 + (size_t)slot * RAWB;
+            for (int v = ptid; v < nunits; v += 32 * UP_PROD_WARPS) {
+                uint32_t rw[4 * D];  // the unit's 8 D samples, 2 per word (I, Q bytes of a sample stay together)
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(rs + 16 * (v * D + c));
+                    rw[4 * c] = q.x; rw[4 * c + 1] = q.y; rw[4 * c + 2] = q.z; rw[4 * c + 3] = q.w;
+                }
+#pragma unroll
+                for (int p = 0; p < D; ++p) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int wd = 0; wd < 4; ++wd) {
+                        // plane sub-samples 2wd, 2wd+1 of this unit = raw samples D*(2wd) + p, D*(2wd+1) + p
+                        const int sa = D * (2 * wd) + p, sb = D * (2 * wd + 1) + p;
+                        const uint32_t sel = (uint32_t)(2 * (sa & 1)) | ((uint32_t)(2 * (sa & 1) + 1) << 4) |
+                                             ((uint32_t)(4 + 2 * (sb & 1)) << 8) | ((uint32_t)(5 + 2 * (sb & 1)) << 12);
+                        o[wd] = __byte_perm(rw[sa >> 1], rw[sb >> 1], sel);
+                    }
+                    *reinterpret_cast<uint4 *>(st_g + (size_t)p * PLB + 16 * v) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            fence_proxy_async();  // plain stores -> visible to the tensor core's (async proxy) operand reads
+            mbar_arrive(full_bar(stage));
+            if (++stage == NST) { stage = 0; ph ^= 1u; }
+            if (++slot == UP_RAW) slot = 0;
+        }
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (warp == UP_MMA_WARP) {
+        // ================= MMA issuer: D phases x KS k-steps into one accumulator set =================
+        const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
+        const uint64_t bdesc0 = smem_desc(tab_s, 128, 256, 0);
+        int stage = 0, as = 0;
+        uint32_t ph = 0, aph = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride) {
+            mbar_wait(full_bar(stage), ph);
+            mbar_wait(acce_bar(as), aph ^ 1u);
+            tc_fence_after();
+            if (elect_one()) {
+                // running descriptors (two 64-bit adds of constants per MMA on the uniform datapath)
+                uint64_t ap = smem_desc(stage0 + (uint32_t)stage * SB, 16, 128, 0);  // plane 0
+                uint64_t bd = bdesc0;
+                const uint32_t d0 = tmem + (uint32_t)(as * N);
+                const uint64_t pstep = (uint64_t)(PLB >> 4);
+                umma_i8c<false>(d0, ap, bd, idesc);
+                for (int kk = 1; kk < KS; ++kk) {
+                    bd += (N * 32) >> 4;
+                    umma_i8c<true>(d0, ap + 2 * kk, bd, idesc);
+                }
+#pragma unroll 1
+                for (int p = 1; p < D; ++p) {
+                    ap += pstep;
+                    for (int kk = 0; kk < KS; ++kk) {
+                        bd += (N * 32) >> 4;
+                        umma_i8c<true>(d0, ap + 2 * kk, bd, idesc);
+                    }
+                }
+                umma_commit(empty_bar(stage));
+                umma_commit(accf_bar(as));
+            }
+            __syncwarp();
+            if (++stage == NST) { stage = 0; ph ^= 1u; }
+            if (++as == UP_SETS) { as = 0; aph ^= 1u; }
+        }
+    } else {
+        // ================= epilogue: warpgroup wg takes every 4th tile, accumulator set wg =================
+        const int ew = warp - UP_EPI_WARP0, wg = ew >> 2, quad = warp & 3;  // warpgroup wg: sets wg, wg + 2
+        const float sc0 = a.sc[0], sc2 = a.sc[2];
+        const int c10[2] = {a.magic[0][0], a.magic[1][0]}, m2[2] = {a.magic[0][2], a.magic[1][2]};
+        uint32_t aph = 0;
+        long long it = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
+            if ((it & 1) != wg) continue;
+            const int set = (int)(it & (UP_SETS - 1));
+            const int ch = (int)(w / a.ntiles);
+            const long long m0 = (w % a.ntiles) * (long long)UP_TILE_OUT;
+            float2 *out = (float2 *)f.out + (long long)ch * f.out_stride;
+            mbar_wait(accf_bar(set), aph);
+            if (set >= 2) aph ^= 1u;  // this warpgroup's two sets alternate; the parity flips after both were used
+            tc_fence_after();
+            uint32_t e[2][3][8];
+            const uint32_t col = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(set * N);
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int dg = 0; dg < 3; ++dg) tmem_ld_16x256b_x2(col + ((uint32_t)(16 * hh) << 16) + dg * 16, e[hh][dg]);
+            tmem_ld_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acce_bar(set));
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                for (int cg = 0; cg < 2; ++cg)
+#pragma unroll
+                    for (int rs = 0; rs < 2; ++rs) {
+                        const int i0 = 4 * cg + 2 * rs;
+                        const long long m = m0 + 8 * (quad * 32 + 16 * hh + 8 * rs + (lane >> 2)) + 4 * cg + (lane & 3);
+                        if (m < f.n_out) {
+                            const float fI = (float)((int)(e[hh][1][i0] << 8) + (int)e[hh][0][i0] + c10[0]);
+                            const float fQ = (float)((int)(e[hh][1][i0 + 1] << 8) + (int)e[hh][0][i0 + 1] + c10[1]);
+                            const float gI = __int_as_float((int)e[hh][2][i0] + m2[0]) - 12582912.0f;
+                            const float gQ = __int_as_float((int)e[hh][2][i0 + 1] + m2[1]) - 12582912.0f;
+                            out[m] = make_float2(fmaf(gI, sc2, fI * sc0), fmaf(gQ, sc2, fQ * sc0));
+                        }
+                    }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == UP_MMA_WARP) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+    }
+}
+
 // balanced base-256 digits of t: t = d0 + 256 d1 + 65536 d2, d0, d1 in [-128, 127]; false if d2 leaves that range
 inline bool digits3(long long t, int d[3]) {
     for (int i = 0; i < 2; ++i) {
@@ -705,6 +961,12 @@ bool fir_umma_geometry(int K, int D, bool taps_complex, bool want_planar, int *R
     const char *e = std::getenv("SDR_UMMA_P");
     const int forced = e ? std::atoi(e) : 0;
     *planar_out = 0;
+    static const bool no_poly = std::getenv("SDR_UMMA_NO_POLY") != nullptr;  // A/B switch (tuning)
+    if (!want_planar && !no_poly && (D == 5 || D == 6 || D == 7 || D == 8 || D == 9 || D == 10 || D == 12) &&
+        up_smem_bytes(D, up_ksteps(K, D), 2) <= 220 * 1024) {
+        *R_out = 8; *PC_out = 8; *planar_out = 2;  // polyphase planes
+        return true;
+    }
     if (!taps_complex && want_planar) {
         // real taps: byte planes, rows R bytes = R samples apart
         int R = 0, PC = 0;
@@ -746,7 +1008,8 @@ bool fir_umma_geometry(int K, int D, bool taps_complex, bool want_planar, int *R
 // host: the 8 alignment variants of the Toeplitz tap table.  Layout [delta][kk][canonical N x 32 B block]:
 // element (n, kb) of a block sits at (n/8)*256 + (kb/16)*128 + (n%8)*16 + kb%16 (no-swizzle K-major core matrices).
 // Column n = digit * 2 PC + 2 u + part; candidate u is the output whose oldest sample sits g*u (+ delta) into the row.
-bool fir_umma_build_tables(const float *taps, int K, bool tc, int R, int PC, bool planar, std::vector<uint8_t> &out, int magic[2][3], float sc[3]) {
+bool fir_umma_build_tables(const float *taps, int K, bool tc, int R, int PC, int mode, int D, std::vector<uint8_t> &out, int magic[2][3], float sc[3]) {
+    const bool planar = mode == 1, poly = mode == 2;
     if (K < 1 || K > UM_MAX_K || (planar && tc)) return false;
     const int KS = planar ? fir_umma_planar_ksteps(K, R, PC) : fir_umma_ksteps(K, R, PC), N = (planar ? 3 : 6) * PC, W = tc ? 2 : 1, G = R / PC;
     float cmax = 0.0f;
@@ -791,6 +1054,27 @@ bool fir_umma_build_tables(const float *taps, int K, bool tc, int R, int PC, boo
     }
     const float base = std::ldexp(1.0f, -S - 7);
     sc[0] = base; sc[1] = base * 256.0f; sc[2] = base * 65536.0f;
+    if (poly) {
+        // [delta][phase][kk][canonical 48 x 32 B block]: column dg*16 + 2c + part, byte kb = sub-sample kb/2 (I, Q)
+        const int KSP = up_ksteps(K, D);
+        out.assign((size_t)8 * D * KSP * 48 * 32, 0);
+        for (int delta = 0; delta < 8; ++delta)
+            for (int ph = 0; ph < D; ++ph)
+                for (int kk = 0; kk < KSP; ++kk) {
+                    uint8_t *blk = out.data() + (((size_t)delta * D + ph) * KSP + kk) * 48 * 32;
+                    for (int n = 0; n < 48; ++n) {
+                        const int dg = n / 16, c = (n % 16) / 2, part = n & 1;
+                        for (int kb = 0; kb < 32; ++kb) {
+                            const int kap = kk * 16 + kb / 2, q = kb & 1;
+                            const int t = kap - c, j = D * t + ph - delta;  // raw offset of this sub-sample from the window start
+                            int v = 0;
+                            if (t >= 0 && j >= 0 && j < K) v = digit(K - 1 - j, part, q, dg);
+                            blk[(n / 8) * 256 + (kb / 16) * 128 + (n % 8) * 16 + kb % 16] = (uint8_t)(int8_t)v;
+                        }
+                    }
+                }
+        return true;
+    }
     out.assign((size_t)8 * KS * N * 32, 0);
     for (int delta = 0; delta < 8; ++delta)
         for (int kk = 0; kk < KS; ++kk) {
@@ -812,8 +1096,62 @@ bool fir_umma_build_tables(const float *taps, int K, bool tc, int R, int PC, boo
 }
 
 // returns SDR_ERR_UNSUPPORTED when this path does not apply (caller falls back to the mma.sync / CUDA-core kernels)
-int fir_umma_launch(const FirArgs &f, int R, int PC, bool planar, const uint8_t *d_tables, const int magic[2][3], const float sc[3], cudaStream_t st) {
+static int fir_umma_poly_launch(const FirArgs &f, const uint8_t *d_tables, const int magic[2][3], const float sc[3], cudaStream_t st) {
+    const int D = f.D, KS = up_ksteps(f.K, D);
+    int stages = UM_STAGES;
+    while (stages > 2 && up_smem_bytes(D, KS, stages) > 222 * 1024) --stages;
+    const size_t smem = up_smem_bytes(D, KS, stages);
+    if (smem > 222 * 1024) return SDR_ERR_UNSUPPORTED;
+    UmArgs a;
+    a.f = f;
+    a.KS = KS;
+    a.stages = stages;
+    long long d = (f.first - (f.K - 1)) % 8;
+    if (d < 0) d += 8;
+    a.delta = (int)d;
+    a.tab = d_tables + (size_t)d * D * KS * 48 * 32;
+    a.stage_bytes = D * 2 * up_nsub(KS);
+    a.n_rows = 0;
+    a.dmagic = 0;
+    a.ntiles = (int)((f.n_out + UP_TILE_OUT - 1) / UP_TILE_OUT);
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 3; ++j) a.magic[i][j] = magic[i][j];
+    for (int j = 0; j < 3; ++j) a.sc[j] = sc[j];
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const long long nwork = (long long)a.ntiles * f.n_ch;
+    const unsigned grid = (unsigned)std::min<long long>(nwork, sms);
+    auto go = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e);
+        kern<<<grid, UP_THREADS, smem, st>>>(a);
+        count_launch();
+        return launch_status();
+    };
+    switch (D) {
+        case 5: return go(fir_umma_poly_kernel<5>);
+        case 6: return go(fir_umma_poly_kernel<6>);
+        case 7: return go(fir_umma_poly_kernel<7>);
+        case 8: return go(fir_umma_poly_kernel<8>);
+        case 9: return go(fir_umma_poly_kernel<9>);
+        case 10: return go(fir_umma_poly_kernel<10>);
+        case 12: return go(fir_umma_poly_kernel<12>);
+    }
+    return SDR_ERR_UNSUPPORTED;
+}
+
+int fir_umma_launch(const FirArgs &f, int R, int PC, int mode, const uint8_t *d_tables, const int magic[2][3], const float sc[3], cudaStream_t st) {
+    const bool planar = mode == 1;
     if (f.n_out <= 0) return SDR_OK;
+    if (mode == 2) {
+        if (f.K > UM_MAX_K || ((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 7) || ((uintptr_t)f.hist & 1) || (f.n_ch > 1 && (f.in_stride & 7)))
+            return SDR_ERR_UNSUPPORTED;
+        return fir_umma_poly_launch(f, d_tables, magic, sc, st);
+    }
     if (f.K > UM_MAX_K || (f.D == 1 && R != PC) || (f.D != 1 && !planar && R != 32)) return SDR_ERR_UNSUPPORTED;
     // rows of a multi-channel call must keep the 16-byte alignment of the first one (strides are ignored for one channel)
     if (((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 15) || ((uintptr_t)f.hist & 1) ||

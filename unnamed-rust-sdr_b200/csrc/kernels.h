@@ -40,9 +40,10 @@ int fir_tc_launch(const FirArgs &a, bool taps_complex, const uint2 *d_tables, fl
 // PC = output candidates per row (== R when D == 1).
 int fir_umma_ksteps(int K, int R, int PC);
 bool fir_umma_geometry(int K, int D, bool taps_complex, bool want_planar, int *R, int *PC, int *planar);
-bool fir_umma_build_tables(const float *taps, int K, bool taps_complex, int R, int PC, bool planar,
+// mode: 0 interleaved bytes, 1 planar (real taps, opt-in), 2 polyphase planes (Decimate with D in 5..12)
+bool fir_umma_build_tables(const float *taps, int K, bool taps_complex, int R, int PC, int mode, int D,
                            std::vector<uint8_t> &out, int magic[2][3], float sc[3]);
-int fir_umma_launch(const FirArgs &a, int R, int PC, bool planar, const uint8_t *d_tables, const int magic[2][3],
+int fir_umma_launch(const FirArgs &a, int R, int PC, int mode, const uint8_t *d_tables, const int magic[2][3],
                     const float sc[3], cudaStream_t st);
 
 // ---------------------------------------------------------------------------------------
