@@ -719,8 +719,10 @@ __host__ __device__ constexpr size_t up_smem_bytes(int D, int KS, int stages) {
     return (size_t)(stages + UP_RAW) * D * 2 * up_nsub(KS) + (size_t)D * KS * 48 * 32 + 1024 + 256;
 }
 
-// roles: 8 producer warps (the phase split is the heavy part here), 1 MMA warp, 8 epilogue warps (a tile has one piece)
-constexpr int UP_PROD_WARPS = 8, UP_MMA_WARP = UP_PROD_WARPS, UP_EPI_WARP0 = UP_PROD_WARPS + 1, UP_THREADS = (UP_PROD_WARPS + 1 + 8) * 32;
+// roles: 8 producer warps (the phase split is the heavy part here), 2 MMA warps taking alternate tiles (a small-N
+// tcgen05.mma costs its issuing thread ~45-80 cycles: one issuer left the tensor pipe 80 % idle), 8 epilogue warps
+constexpr int UP_PROD_WARPS = 8, UP_MMA_WARP = UP_PROD_WARPS, UP_MMA_WARPS = 2, UP_EPI_WARP0 = UP_PROD_WARPS + UP_MMA_WARPS,
+              UP_THREADS = (UP_PROD_WARPS + UP_MMA_WARPS + 8) * 32;
 
 template <int D>
 __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmArgs a) {
@@ -845,13 +847,16 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
             if (++slot == UP_RAW) slot = 0;
         }
         asm volatile("cp.async.wait_all;" ::: "memory");
-    } else if (warp == UP_MMA_WARP) {
-        // ================= MMA issuer: D phases x KS k-steps into one accumulator set =================
+    } else if (warp < UP_EPI_WARP0) {
+        // ================= MMA issuers: warp j takes tiles j, j + 2, ...; D phases x KS k-steps into one set =================
+        const int mw = warp - UP_MMA_WARP;
         const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         const uint64_t bdesc0 = smem_desc(tab_s, 128, 256, 0);
-        int stage = 0, as = 0;
-        uint32_t ph = 0, aph = 0;
-        for (long long w = blockIdx.x; w < nwork; w += wstride) {
+        long long it = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
+            if ((it & (UP_MMA_WARPS - 1)) != mw) continue;
+            const int stage = (int)(it % NST), as = (int)(it & (UP_SETS - 1));
+            const uint32_t ph = (uint32_t)((it / NST) & 1), aph = (uint32_t)((it / UP_SETS) & 1);
             mbar_wait(full_bar(stage), ph);
             mbar_wait(acce_bar(as), aph ^ 1u);
             tc_fence_after();
@@ -878,8 +883,6 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
                 umma_commit(accf_bar(as));
             }
             __syncwarp();
-            if (++stage == NST) { stage = 0; ph ^= 1u; }
-            if (++as == UP_SETS) { as = 0; aph ^= 1u; }
         }
     } else {
         // ================= epilogue: warpgroup wg takes every 4th tile, accumulator set wg =================
