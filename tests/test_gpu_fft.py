@@ -145,3 +145,35 @@ def test_c2_full_size_parseval_and_spot_checks(sdr):
     for b in (0, 1, 4097, batches // 2 + 3, batches - 1):
         x = O.unpack_u8iq(raw[2 * n * b:2 * n * (b + 1)].cpu().numpy()).reshape(1, n)
         check(out[b:b + 1].cpu().numpy(), x, shift=True, norm=True)
+
+
+@pytest.mark.parametrize("logn", [13, 14, 16])
+def test_c5_full_size_parseval_and_spot_checks(sdr, logn):
+    """BASELINE config 5 at full size: 1 GiB of complex f32 per GPU (2^27 samples), N = 8192 / 16384 / 65536, device
+    resident.  Parseval per transform (f64 on the device), spot transforms against the f64 DFT, and linearity:
+    FFT(x) for x -> 2x scales exactly (power of two)."""
+    import torch
+    n = 1 << logn
+    batches = (1 << 27) // n
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(100 + logn)
+    x = torch.empty((batches, n), dtype=torch.complex64, device=dev)
+    x.view(torch.float32).uniform_(-1, 1, generator=g)
+    out = torch.empty_like(x)
+    plan = sdr.FftPlan(n, "c64", shift=True, norm=True)
+    plan.exec_dev(x, batches, out)
+    torch.cuda.synchronize()
+    step = max(1, batches // 8)
+    for lo in range(0, batches, step):
+        xi = x[lo:lo + step]
+        e_in = (xi.real.double() ** 2 + xi.imag.double() ** 2).sum(dim=1)
+        o = out[lo:lo + step]
+        e_out = (o.real.double() ** 2 + o.imag.double() ** 2).sum(dim=1)
+        assert float(((e_out - e_in).abs() / e_in).max()) < 1e-5
+    for b in (0, 1, batches // 2 + 1, batches - 1):
+        check(out[b:b + 1].cpu().numpy(), x[b:b + 1].cpu().numpy(), shift=True, norm=True)
+    spot = out[batches // 3].clone()
+    x.mul_(2.0)
+    plan.exec_dev(x, batches, out)
+    torch.cuda.synchronize()
+    assert torch.equal(out[batches // 3].view(torch.float32), (spot * 2.0).view(torch.float32))

@@ -320,3 +320,28 @@ def test_fir_full_size_linearity_and_device_path(sdr):
     got = f2.process_dev(iq[2 * (half - 64):], half + 64, o2, half + 64)
     torch.cuda.synchronize()
     assert got == half + 64 and torch.equal(o2[64:].view(torch.float32), out[half:].view(torch.float32))
+
+
+def test_c3_full_size_decimated_equals_every_tenth_output(sdr):
+    """BASELINE config 3's FIR stage at 2^26 samples, device resident: the fused Decimate (polyphase tcgen05 kernel) must
+    equal every 10th output of the undecimated filter.  Both kernels accumulate exact integers and share the epilogue
+    arithmetic, so the comparison is bit for bit; spot windows are checked against the f64 truth."""
+    import torch
+    n, D = 1 << 26, 10
+    taps = gen.lowpass_taps(255, 100e3, 2.4e6)
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(4321)
+    iq = torch.randint(0, 256, (2 * n,), dtype=torch.uint8, device=dev, generator=g)
+    full = torch.empty(n, dtype=torch.complex64, device=dev)
+    dec = torch.empty(n // D + 1, dtype=torch.complex64, device=dev)
+    f1, fd = sdr.Fir(taps, "u8iq"), sdr.Fir(taps, "u8iq", decimation=D)
+    assert f1.process_dev(iq, n, full, n) == n
+    got = fd.process_dev(iq, n, dec, n // D + 1)
+    torch.cuda.synchronize()
+    assert f1.last_path == 4 and fd.last_path == 4 and got == n // D
+    assert torch.equal(dec[:got].view(torch.float32), full[D - 1::D][:got].contiguous().view(torch.float32))
+    for s in (0, 3333333, n // D - 4000):
+        lo = max(0, s * D + D - 1 - 254)
+        seg = iq[2 * lo:2 * ((s + 3000) * D + D)].cpu().numpy()
+        want = O.fir_f64(taps, O.unpack_u8iq(seg))[(s * D + D - 1 - lo)::D][:3000]
+        assert rel_err(dec[s:s + 3000].cpu().numpy(), want) < 1e-6
