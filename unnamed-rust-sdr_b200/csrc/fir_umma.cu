@@ -1,4 +1,7 @@
-// fir_umma.cu -- K5: fused u8-IQ FIR on the 5th-generation tensor cores (tcgen05 / TMEM), D == 1.
+// fir_umma.cu -- K5: fused u8-IQ FIR (+ Decimate) on the 5th-generation tensor cores (tcgen05 / TMEM).
+//
+// Three kernels: fir_umma_kernel (interleaved bytes; D == 1 and decimation by candidate offsets), fir_umma_poly_kernel
+// (decimation on phase planes, D in 5..12) and the opt-in fir_umma_planar_kernel (real taps on I / Q byte planes).
 //
 // Same reference functions as fir.cu: RtlTcpSignal::next -> signal::Filter::next -> Fir::apply
 // (src/rtltcp.rs:158-164, src/signal/adapters/mod.rs:94-96, src/filter/fir.rs:23-32, src/filter/convolve.rs:13-15).
@@ -18,9 +21,10 @@
 //     output P*i + j.  Real taps touch only the I (or Q) bytes of the window; complex taps touch both
 //     (y.re = x.re c.re - x.im c.im, y.im = x.re c.im + x.im c.re: the signs live in the table).
 //   * D (TMEM, s32): exact integer sums.  |sum| <= 255*128*K < 2^31 and |sum - 128 sum_k d| <= 2^14 K < 2^23 for
-//     K <= 511, so the epilogue converts with the 1.5*2^23 magic-number add (no I2F) and combines the three digits with
-//     two FFMAs: the result is the exactly-accumulated dot product rounded ~once -- closer to the f64 truth than the
-//     reference's own sequential f32 sum (tests/test_gpu_fir.py bars: 1e-5 relative, and <= 4x the reference's error).
+//     K <= 511, so the epilogue combines digits 0 and 1 in s32, converts (one I2F, and the 1.5*2^23 magic-number add for
+//     digit 2) and joins them with one FFMA: the result is the exactly-accumulated dot product rounded ~once -- closer
+//     to the f64 truth than the reference's own sequential f32 sum (tests/test_gpu_fir.py bars: 1e-5 relative, and
+//     <= 4x the reference's error), and independent of how the stream is cut into calls.
 //
 // Decimation (signal::Decimate fused behind the filter, src/signal/adapters/mod.rs:30-37): rows stay R = 32 samples
 // apart (a matrix descriptor cannot step by D), and the B columns are the CANDIDATE offsets inside a row at which a
@@ -31,8 +35,8 @@
 // Warp roles (one persistent CTA per SM, 640 threads):
 //   warps 0..2  producers: cp.async 16-byte chunks global -> (swizzled) stage, completion on an mbarrier
 //                          (cp.async.mbarrier.arrive.noinc); history / zero padding at the stream start by plain stores
-//   warp 3      MMA issuer: one lane issues KS * MB tcgen05.mma.kind::i8 per tile, tcgen05.commit frees the stage and
-//                          publishes the accumulator set
+//   warp 3      MMA issuer: one elected lane (elect.sync) issues KS * MB tcgen05.mma.kind::i8 per tile with running
+//                          descriptors; tcgen05.commit frees the stage and publishes the accumulator set
 //   warps 4..19 four epilogue warpgroups (two accumulator sets x two halves of a tile): tcgen05.ld.16x256b fragments ->
 //               digits -> f32 -> global stores straight from registers (4 threads = one 32-byte sector)
 #include <algorithm>
