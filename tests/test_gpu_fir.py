@@ -345,3 +345,37 @@ def test_c3_full_size_decimated_equals_every_tenth_output(sdr):
         seg = iq[2 * lo:2 * ((s + 3000) * D + D)].cpu().numpy()
         want = O.fir_f64(taps, O.unpack_u8iq(seg))[(s * D + D - 1 - lo)::D][:3000]
         assert rel_err(dec[s:s + 3000].cpu().numpy(), want) < 1e-6
+
+
+def test_tensor_paths_random_configurations(sdr):
+    """Randomised sweep over (K, D, tap kind, channels, length, blocking): every fast path against the f64 truth, and --
+    where the tcgen05 path ran -- bit-identical results for a second, differently cut pass over the same stream."""
+    rng = np.random.default_rng(20261018)
+    seen = {1: 0, 3: 0, 4: 0}
+    for trial in range(48):
+        K = int(rng.choice([1, 2, 7, 33, 64, 100, 255, 300, 511, 600]))
+        D = int(rng.choice([1, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 16, 25]))
+        tc = bool(rng.integers(0, 2))
+        n_ch = int(rng.choice([1, 1, 2, 3]))
+        n = int(rng.choice([1, 5, 100, 1023, 4096, 10240, 30011]))
+        taps = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+        if tc:
+            taps = (taps + 1j * rng.standard_normal(K) / np.sqrt(K)).astype(np.complex64)
+        raw = gen.random_u8(2 * n_ch * n, 7000 + trial).reshape(n_ch, 2 * n)
+        f = sdr.Fir(taps, "u8iq", decimation=D, n_channels=n_ch)
+        cut = int(rng.integers(0, n + 1))
+        parts = [f.process(np.ascontiguousarray(raw[:, :2 * cut])), f.process(np.ascontiguousarray(raw[:, 2 * cut:]))]
+        got = np.concatenate([p_.reshape(n_ch, -1) for p_ in parts], axis=1)
+        assert got.shape == (n_ch, n // D), (trial, K, D, n, got.shape)
+        seen[f.last_path] = seen.get(f.last_path, 0) + 1
+        for c in range(n_ch):
+            truth = O.fir_f64(taps, O.unpack_u8iq(raw[c]))[D - 1::D]
+            if len(truth):
+                assert rel_err(got[c], truth) < (1e-6 if f.last_path == 4 else TOL), (trial, K, D, tc, n_ch, n, f.last_path)
+        if f.last_path == 4 and n > 0:
+            f.reset()
+            cut2 = int(rng.integers(0, n + 1))
+            again = np.concatenate([p_.reshape(n_ch, -1) for p_ in (f.process(np.ascontiguousarray(raw[:, :2 * cut2])),
+                                                                    f.process(np.ascontiguousarray(raw[:, 2 * cut2:])))], axis=1)
+            assert np.array_equal(again.view(np.uint32), got.view(np.uint32)), (trial, K, D, n)
+    assert seen[4] >= 20  # the tcgen05 kernels carry most configurations
