@@ -151,7 +151,7 @@ import gen, sdr_b200 as sdr
 x = gen.complex_noise(30000, 12).view(np.float32).reshape(-1, 2)
 outs = []
 for typ in (0, 1, 2):
-    for ratio in (0.2, 0.08, 0.5, 2.0):
+    for ratio in (0.2, 0.08, 0.5, 2.0, 0.25, 0.0625, 16.0 / 3.0):
         for ch in (1, 2):
             a = sdr.SampleRate(typ, ch)
             xx = x if ch == 2 else x[:, :1]
@@ -161,16 +161,26 @@ for typ in (0, 1, 2):
                 pos += u
                 outs.append(np.array([u, len(o)], np.float32))
                 outs.append(o.ravel())
+# one long call: the size at which the library itself picks the R-outputs-per-thread kernel
+xl = gen.complex_noise(260000, 13).view(np.float32).reshape(-1, 2)
+for typ, ratio in ((0, 0.2), (2, 0.5), (1, 0.25)):
+    a = sdr.SampleRate(typ, 2)
+    u, o = a.process(ratio, xl, 140000)
+    outs.append(np.array([u, len(o)], np.float32))
+    outs.append(o.ravel())
 np.save(sys.argv[1], np.concatenate(outs))
 """ % (os.path.join(os.path.dirname(__file__), "..", "unnamed-rust-sdr_b200"), os.path.dirname(__file__))
     res = []
-    for env_extra in ({}, {"SDR_SRC_NO_POLY": "1"}):
+    # SDR_SRC_R forces the R-outputs-per-thread variant that long calls take (the calls here are short)
+    for env_extra in ({}, {"SDR_SRC_NO_POLY": "1"}, {"SDR_SRC_R": "5"}, {"SDR_SRC_R": "3"}):
         with tempfile.NamedTemporaryFile(suffix=".npy") as f:
             env = dict(os.environ, **env_extra)
             subprocess.check_call([sys.executable, "-c", code, f.name], env=env)
             res.append(np.load(f.name))
-    assert res[0].shape == res[1].shape and res[0].size > 100000
-    assert np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32))
+    assert res[0].size > 100000
+    for r in res[1:]:
+        assert r.shape == res[0].shape
+        assert np.array_equal(res[0].view(np.uint32), r.view(np.uint32))
 
 
 def test_samplerate_contract(sdr):
@@ -262,3 +272,40 @@ def test_pll_filter_adaptor(sdr):
     out = f.collect()
     assert len(out) == 1890
     compare_pll(out, f.locked, g["pll_out"], g["pll_locked"], 1.8e6, 0.035, 1e-3, "adaptor")
+
+
+def test_samplerate_handles_on_two_streams_share_the_constant_table_safely(sdr):
+    """The long-call sinc kernel reads its coefficients from one __constant__ table per device.  Two converters of
+    different quality on two streams, launched back to back without synchronising in between, must each see their
+    own table: results equal the same calls made one at a time."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n_in = 200000
+    x = gen.complex_noise(n_in, 21).view(np.float32).reshape(-1, 2)
+    d_in = torch.from_numpy(x).to(dev)
+    cfgs = [(0, 0.2), (2, 0.5), (1, 0.25), (2, 0.2)]
+    # one at a time
+    want = []
+    for typ, ratio in cfgs:
+        s = sdr.SampleRate(typ, 2)
+        out = torch.zeros((int(n_in * ratio) + 64, 2), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        used, got = s.process_dev(ratio, d_in, n_in, out, out.shape[0])
+        torch.cuda.synchronize()
+        want.append((used, got, out[:got].cpu().numpy()))
+    # interleaved on separate streams, several rounds, no synchronisation between launches
+    streams = [torch.cuda.Stream(dev) for _ in cfgs]
+    torch.cuda.synchronize()
+    for _ in range(3):
+        outs, hs = [], []
+        for (typ, ratio), st in zip(cfgs, streams):
+            s = sdr.SampleRate(typ, 2, stream=st)
+            out = torch.zeros((int(n_in * ratio) + 64, 2), dtype=torch.float32, device=dev)
+            st.wait_stream(torch.cuda.current_stream(dev))
+            used, got = s.process_dev(ratio, d_in, n_in, out, out.shape[0])
+            outs.append((used, got, out))
+            hs.append(s)
+        torch.cuda.synchronize()
+        for (used, got, out), (wu, wg, wo) in zip(outs, want):
+            assert (used, got) == (wu, wg)
+            assert np.array_equal(out[:got].cpu().numpy().view(np.uint32), wo.view(np.uint32))

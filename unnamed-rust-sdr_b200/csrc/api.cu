@@ -1315,7 +1315,7 @@ static int src_process_impl(sdr_src *s, SDR_SRC_DATA *d, bool dev_ptrs) {
         dout = (float *)s->d_out.p;
     }
     L.out = dout;
-    if ((size_t)(wc + 2) * 32 * sizeof(double) <= ((size_t)32 << 20) && s->coef.reserve((size_t)(wc + 2) * 32 * sizeof(double)) == SDR_OK)
+    if ((size_t)(wc + 6) * 64 * sizeof(double) <= ((size_t)64 << 20) && s->coef.reserve((size_t)(wc + 6) * 64 * sizeof(double)) == SDR_OK)
         L.coef = (double *)s->coef.p;
     rc = src_launch(L, st);
     if (rc) return rc;

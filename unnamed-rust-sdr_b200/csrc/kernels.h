@@ -112,7 +112,7 @@ struct SrcLaunch {
     double rq, rho;
     long long wc;
     // polyphase fast path (filled by src_launch when the positions are exact): device scratch for the per-phase wing
-    // coefficients, 2 * 16 * (wc + 2) doubles, or null to force the per-tap kernel
+    // coefficients, 2 copies * 2 wings * 16 phases * (wc + 6) doubles, or null to force the per-tap kernel
     double *coef = nullptr;
 };
 int src_launch(const SrcLaunch &s, cudaStream_t st);
