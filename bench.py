@@ -262,7 +262,44 @@ def wl_channelizer(torch, sdr, dev, n_ch=128, log2_n=16, fast=False):
                 kernel="fir_rb_kernel+pll_kernel", desc="%d channels x (255-tap FIR + PLL)" % n_ch)
 
 
+def wl_fm(torch, sdr, dev, n_st=128, log2_n=18, fast=False):
+    """the FM stereo receiver of src/main.rs:32-81 for a batch of stations, device resident."""
+    n = 1 << log2_n
+    row = 2 * n
+    g = torch.Generator(device=dev).manual_seed(0x5D12B200 + 9)
+    raw = torch.randint(0, 256, (n_st, row), dtype=torch.uint8, device=dev, generator=g)
+    fm = sdr.FmStereo(n_st, 1.8e6, fast_math=fast, device=dev.index, stream=torch.cuda.current_stream(dev))
+    cap = fm.max_output(n)
+    out = torch.empty((n_st, cap, 2), dtype=torch.float32, device=dev)
+
+    def step():
+        fm.process_dev(raw, n, row, out, cap, cap, end_of_input=False)
+
+    def cpu(units, threads):
+        import oracle_lib as O
+        import gen
+        m = max(4096, units)
+        x = gen.complex_noise(m, 3)
+        p = O.Pll(O.pll_design(0.0, 0.035, (O.BQ_LOWPASS, 80000.0, 0.7), (O.BQ_IDENTITY, 0.0, 0.0),
+                               (O.BQ_LOWPASS, 20000.0, 0.7)), 1.8e6)
+        t0 = time.perf_counter()
+        p.apply(x)  # the demodulator PLL alone: > 90 % of the chain's CPU time, one thread (the loop is sequential)
+        return time.perf_counter() - t0
+
+    return dict(name="fm_stereo_%dst_2p%d%s" % (n_st, log2_n, "_fastmath" if fast else ""), units=n_st * n,
+                bytes_per_unit=2.0 + 8.0 / 37.5, step=step, e2e_setup=None, e2e_step=None, h2d=2 * n_st * n,
+                d2h=8 * n_st * cap, cpu=cpu, dtype="f32 (f64 atan2/sincos in the PLLs, f64 sinc accumulation)",
+                kernel="pll_kernel + src_sinc + pll_stereo_kernel + biquad_kernel",
+                desc="%d stations x FM stereo receiver (main.rs:32-81)" % n_st)
+
+
 def make_workload(name, torch, sdr, dev):
+    if name == "fm":
+        return wl_fm(torch, sdr, dev)
+    if name == "fmfast":
+        return wl_fm(torch, sdr, dev, fast=True)
+    if name == "fm1024":
+        return wl_fm(torch, sdr, dev, n_st=1024, log2_n=16)
     if name in ("c2", "fft1024_u8", "default"):
         return wl_fft1024_u8(torch, sdr, dev)
     if name == "c2_small":

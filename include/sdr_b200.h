@@ -202,6 +202,14 @@ int sdr_pll_process(sdr_pll_t *, const float *in_c64, size_t n, size_t in_stride
                     uint8_t *locked, size_t out_stride);
 int sdr_pll_process_dev(sdr_pll_t *, const float *in_c64, size_t n, size_t in_stride, float *out,
                         uint8_t *locked, size_t out_stride);
+/* FM stereo decode around a pilot-tone Pll -- the closure of src/main.rs:62-71:
+ *     mono = v * 0.5;  diff = Some(_) = pll.apply(Complex::new(v, 0.0)) ? (v / pll.value.powi(2)).re * 0.5 : 0.0
+ * v: n_streams rows of n f32 samples (row stride in_stride samples); out_mono_diff: rows of n
+ * (mono, diff) frames (row stride out_stride frames).  Advances the same carried state as process. */
+int sdr_pll_stereo_decode(sdr_pll_t *, const float *v, size_t n, size_t in_stride, float *out_mono_diff,
+                          size_t out_stride);
+int sdr_pll_stereo_decode_dev(sdr_pll_t *, const float *v, size_t n, size_t in_stride, float *out_mono_diff,
+                              size_t out_stride);
 /* the public fields Pll::nphase / Pll::value (pll.rs:21-22) of one stream; synchronises */
 int sdr_pll_get_state(sdr_pll_t *, size_t stream_index, float *nphase, float *value_re, float *value_im);
 
@@ -300,6 +308,73 @@ int sdr_timer_begin(sdr_timer_t *);
 int sdr_timer_end(sdr_timer_t *, float *elapsed_ms); /* synchronises the stream */
 /* count of kernels this library has launched in this process (all handles) */
 uint64_t sdr_kernel_launch_count(void);
+
+/* ======================================================================================
+ * FM broadcast stereo receiver -- the signal chain of src/main.rs:32-81 for a batch of
+ * stations, every intermediate device-resident:
+ *   u8 IQ (rtltcp.rs:158-164) -> Pll demodulator (main.rs:41-49) -> / 75000 -> resample_with(
+ *   SincFastest, 144 kHz) (main.rs:50) -> pilot Pll + (mono, diff) decode (main.rs:54-71) ->
+ *   resample(48 kHz) (main.rs:73) -> Lr de-emphasis + (mono+diff, mono-diff) (main.rs:52,75-80).
+ * Carried state: both PLLs, both converters and the de-emphasis filters of every station, so a
+ * stream may be fed in calls of any size.
+ * ====================================================================================== */
+typedef struct {
+    size_t n_stations;
+    float rate;     /* input sample rate; main.rs:32 uses 1 800 000 */
+    float pilot;    /* pilot tone in Hz; 0 selects main.rs:54's 19 000 */
+    unsigned flags; /* SDR_PLL_FAST_MATH */
+    int device;
+    void *stream;
+} sdr_fm_config_t;
+
+typedef struct sdr_fm sdr_fm_t;
+sdr_fm_t *sdr_fm_create(const sdr_fm_config_t *cfg, int *err);
+void sdr_fm_destroy(sdr_fm_t *);
+int sdr_fm_reset(sdr_fm_t *);
+float sdr_fm_output_rate(const sdr_fm_t *);          /* 48000 */
+size_t sdr_fm_max_output(const sdr_fm_t *, size_t n); /* an out_cap that is always enough for n input samples */
+/* iq: n_stations rows of n u8 IQ samples (2n bytes each, row stride in_stride BYTES);
+ * out: n_stations rows of (left, right) f32 frames at 48 kHz, capacity out_cap frames per row,
+ * row stride out_stride frames; *n_out = frames written per row (the same for every station).
+ * end_of_input != 0 flushes the converters the way signal::Resample does at the end of its
+ * upstream (adapters/resample.rs:45-65).  _dev: iq / out are device pointers, rows 16-byte
+ * aligned (in_stride % 16 == 0 when n_stations > 1), samples land asynchronously on the stream. */
+int sdr_fm_process(sdr_fm_t *, const uint8_t *iq, size_t n, size_t in_stride, float *out, size_t out_cap,
+                   size_t out_stride, size_t *n_out, int end_of_input);
+int sdr_fm_process_dev(sdr_fm_t *, const uint8_t *iq, size_t n, size_t in_stride, float *out, size_t out_cap,
+                       size_t out_stride, size_t *n_out, int end_of_input);
+
+/* ======================================================================================
+ * sliding-window spectra -- the spectrum path of examples/live.rs:30-39:
+ *     sig.window(duration).decimate(fps).map(|w| fft::fft(from_iter(rate, w...)))
+ * Window (src/signal/adapters/mod.rs:271-303) holds the last `window` samples (initially
+ * zeros) and yields after every input sample; Decimate (mod.rs:14-41) keeps every hop-th, so
+ * kept window j ends at input sample (j + 1) * hop - 1; each kept window goes through
+ * fft::fft (src/fft.rs:3-28; flags as sdr_fft_config_t, any length).
+ *   window = sdr_duration_samples(rate, duration),  hop = sdr_decimate_wait(rate, fps)
+ * Carried state: the last window - 1 samples and the stream position.
+ * ====================================================================================== */
+typedef struct {
+    size_t window;    /* samples per window = transform length */
+    size_t hop;       /* Decimate's wait D >= 1 */
+    int input_format; /* U8IQ or C64 */
+    unsigned flags;   /* SDR_FFT_SHIFT | SDR_FFT_NORM */
+    int device;
+    void *stream;
+} sdr_window_fft_config_t;
+
+typedef struct sdr_window_fft sdr_window_fft_t;
+sdr_window_fft_t *sdr_window_fft_create(const sdr_window_fft_config_t *cfg, int *err);
+void sdr_window_fft_destroy(sdr_window_fft_t *);
+int sdr_window_fft_reset(sdr_window_fft_t *);
+size_t sdr_window_fft_size(const sdr_window_fft_t *);
+/* windows the next n_in input samples complete */
+size_t sdr_window_fft_output_count(const sdr_window_fft_t *, size_t n_in);
+/* out_c64: *n_windows consecutive spectra of `window` c64 values each (capacity out_cap windows) */
+int sdr_window_fft_process(sdr_window_fft_t *, const void *in, size_t n_in, float *out_c64, size_t out_cap,
+                           size_t *n_windows);
+int sdr_window_fft_process_dev(sdr_window_fft_t *, const void *in, size_t n_in, float *out_c64, size_t out_cap,
+                               size_t *n_windows);
 
 #ifdef __cplusplus
 }

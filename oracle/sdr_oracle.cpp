@@ -517,6 +517,29 @@ static inline void pll_step(orc_pll *p, float xr, float xi, float *out, uint8_t 
 extern "C" void orc_pll_apply(orc_pll_t *p, const float *in, size_t n, float *out, uint8_t *locked) {
     for (size_t i = 0; i < n; ++i) pll_step(p, in[2 * i], in[2 * i + 1], out + i, locked + i);
 }
+// FM stereo decode closure of src/main.rs:62-71 around a pilot-tone Pll:
+//     let mono = v * 0.5;
+//     let diff = if let Some(_) = pllpilot.apply(Complex::new(v, 0.0)) {
+//         let diffc = v / pllpilot.value.powi(2);  diffc.re * 0.5 } else { 0.0 };
+// num-complex 0.2 (not in the tree, restated from the published crate): powi(2) = z * z by repeated
+// multiplication (num_traits::pow), f32 / Complex = (a*c/|z|^2, -a*d/|z|^2) with |z|^2 = c*c + d*d.
+extern "C" void orc_fm_stereo_decode(orc_pll_t *p, const float *v, size_t n, float *out_mono_diff) {
+    for (size_t i = 0; i < n; ++i) {
+        float o;
+        uint8_t lk;
+        pll_step(p, v[i], 0.0f, &o, &lk);
+        const float mono = v[i] * 0.5f;
+        float diff = 0.0f;
+        if (lk) {
+            const float zr = p->vre * p->vre - p->vim * p->vim;
+            const float zi = p->vre * p->vim + p->vim * p->vre;
+            const float ns = zr * zr + zi * zi;
+            diff = (v[i] * zr / ns) * 0.5f;
+        }
+        out_mono_diff[2 * i] = mono;
+        out_mono_diff[2 * i + 1] = diff;
+    }
+}
 extern "C" void orc_pll_state(const orc_pll_t *p, float *nphase, float *vre, float *vim) {
     *nphase = p->nphase;
     *vre = p->vre;

@@ -105,6 +105,8 @@ void orc_pll_free(orc_pll_t *);
 /* out[i] = output value, locked[i] = 1 iff Some(..) (locked > 0.01) */
 void orc_pll_apply(orc_pll_t *, const float *in_c64, size_t n, float *out, uint8_t *locked);
 void orc_pll_state(const orc_pll_t *, float *nphase, float *value_re, float *value_im);
+/* the stereo-decode closure of src/main.rs:62-71 around a pilot Pll: out = (mono, diff) frames */
+void orc_fm_stereo_decode(orc_pll_t *, const float *v, size_t n, float *out_mono_diff);
 
 /* ---- FreqSweep  (src/signal/sources.rs:116-194) ---------------------------------------- */
 /* freq_sweep(rate, df, warmup, start..end); writes up to cap samples, returns total length */

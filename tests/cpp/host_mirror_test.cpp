@@ -180,6 +180,70 @@ int main() {
         orc_fir_free(of);
     }
 
+    // ---- src/main.rs:32-81 as one device-resident pipeline == the same chain hopping through host buffers stage by stage ----
+    {
+        const size_t n = 180000;  // 0.1 s at 1.8 MS/s
+        std::vector<uint8_t> iq(2 * n);
+        double ph = 0.0;
+        for (size_t i = 0; i < n; ++i) {  // stereo multiplex: L = 1 kHz, R = 3 kHz, 19 kHz pilot, 38 kHz subcarrier
+            const double t = (double)i / 1.8e6;
+            const double l = std::sin(2 * M_PI * 1000 * t), r = std::sin(2 * M_PI * 3000 * t);
+            const double mpx = 0.45 * (l + r) + 0.1 * std::sin(2 * M_PI * 19000 * t) + 0.45 * (l - r) * std::sin(2 * M_PI * 38000 * t);
+            ph += 2 * M_PI * 75000.0 * mpx / 1.8e6;
+            iq[2 * i] = (uint8_t)std::lround(128 + 90 * std::cos(ph));
+            iq[2 * i + 1] = (uint8_t)std::lround(128 + 90 * std::sin(ph));
+        }
+        app::FmStereo fm(1);
+        std::vector<std::pair<float, float>> got;
+        const size_t ngot = fm.process(iq.data(), n, true, got);
+        EXPECT(fm.rate() == 48000.0f && ngot > 4700 && ngot < 4900, "FmStereo output count %zu", ngot);
+
+        // stage by stage with the mirrored reference types, every intermediate in host memory
+        std::vector<Complex> x(n);
+        for (size_t i = 0; i < n; ++i) x[i] = Complex(((float)iq[2 * i] - 128.0f) / 128.0f, ((float)iq[2 * i + 1] - 128.0f) / 128.0f);
+        filter::Pll demod = filter::PllDesign(0.0f, 0.035f, filter::BiquadD::LowPass(80000.0f, 0.7f), filter::BiquadD::Identity(),
+                                              filter::BiquadD::LowPass(20000.0f, 0.7f)).design(1800000.0f);
+        std::vector<std::optional<float>> d;
+        demod.process(x.data(), n, d);
+        std::vector<float> v1(n);
+        for (size_t i = 0; i < n; ++i) v1[i] = d[i].value_or(0.0f) / 75000.0f;
+        auto run_src = [](auto &sr, double ratio, const auto &in, auto &out) {
+            using V = std::decay_t<decltype(out)>;
+            V chunk;
+            chunk.reserve(in.size());
+            sr.process(ratio, in, chunk);
+            out = chunk;
+            for (;;) {  // flush: empty input = end_of_input (resample.rs:56), until nothing comes back
+                V none, more;
+                more.reserve(4096);
+                sr.process(ratio, none, more);
+                if (more.empty()) break;
+                out.insert(out.end(), more.begin(), more.end());
+            }
+        };
+        resample::SampleRate<float> sr1(resample::ConverterType::SincFastest);
+        std::vector<float> v2;
+        run_src(sr1, (double)144000.0f / (double)1800000.0f, v1, v2);
+        filter::Pll pilot = filter::PllDesign(19000.0f, 0.0002f, filter::BiquadD::LowPass(200.0f, 0.7f), filter::BiquadD::LowPass(20.0f, 0.7f),
+                                              filter::BiquadD::LowPass(20.0f, 0.7f)).design(144000.0f);
+        std::vector<std::pair<float, float>> md, md2;
+        pilot.stereo_decode(v2.data(), v2.size(), md);
+        resample::SampleRate<std::pair<float, float>> sr2(resample::ConverterType::SincBestQuality);
+        run_src(sr2, (double)48000.0f / (double)144000.0f, md, md2);
+        std::vector<float> mono(md2.size()), diff(md2.size()), mo, di;
+        for (size_t i = 0; i < md2.size(); ++i) { mono[i] = md2[i].first; diff[i] = md2[i].second; }
+        filter::Biquad<float> dm(filter::BiquadD::Lr(1.0f / (75.0f * 0.001f * 0.001f)), 48000.0f), dd(dm);
+        dm.process(mono.data(), mono.size(), mo);
+        dd.process(diff.data(), diff.size(), di);
+        EXPECT(md2.size() == ngot, "stage-by-stage count %zu vs %zu", md2.size(), ngot);
+        size_t bad = 0;
+        for (size_t i = 0; i < std::min(ngot, md2.size()); ++i) {
+            const float L = mo[i] + di[i], R = mo[i] - di[i];
+            if (std::memcmp(&L, &got[i].first, 4) || std::memcmp(&R, &got[i].second, 4)) ++bad;
+        }
+        EXPECT(bad == 0, "FmStereo vs stage-by-stage chain: %zu frames differ", bad);
+    }
+
     printf(fails ? "HOST MIRROR: %d failure(s)\n" : "HOST MIRROR OK\n", fails);
     return fails ? 1 : 0;
 }

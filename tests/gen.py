@@ -74,3 +74,24 @@ def fm_u8(n, fs, dev, f_audio, sigma, seed, offset=0):
     phase = dev / f_audio * np.sin(2 * np.pi * f_audio * t)
     z = 0.6 * np.exp(1j * phase) + sigma / 0.577 * (noise(n, seed, offset) + 1j * noise(n, seed + 7, offset))
     return quantise_u8iq(z)
+
+
+def fm_stereo_u8(n, fs, f_left, f_right, seed, sigma=0.01, dev=75e3, offset=0):
+    """A broadcast-FM stereo multiplex (L+R, 19 kHz pilot, L-R on the suppressed 38 kHz subcarrier) frequency-
+    modulated onto a baseband carrier, as rtl_tcp bytes: what src/main.rs listens to."""
+    t = np.arange(offset, offset + n, dtype=np.float64) / fs
+    left = np.sin(2 * np.pi * f_left * t)
+    right = np.sin(2 * np.pi * f_right * t)
+    mpx = 0.45 * (left + right) + 0.1 * np.sin(2 * np.pi * 19000.0 * t) + \
+        0.45 * (left - right) * np.sin(2 * np.pi * 38000.0 * t)
+    # phase = 2 pi dev * integral(mpx): closed-form per term keeps chunks (offset) consistent
+    def integ_sin(f):
+        return -np.cos(2 * np.pi * f * t) / (2 * np.pi * f)
+    def integ_sin_sin(fa, fb):  # sin(a) sin(b) = (cos(a-b) - cos(a+b)) / 2
+        return 0.5 * (np.sin(2 * np.pi * (fa - fb) * t) / (2 * np.pi * (fa - fb)) -
+                      np.sin(2 * np.pi * (fa + fb) * t) / (2 * np.pi * (fa + fb)))
+    integral = 0.45 * (integ_sin(f_left) + integ_sin(f_right)) + 0.1 * integ_sin(19000.0) + \
+        0.45 * (integ_sin_sin(f_left, 38000.0) - integ_sin_sin(f_right, 38000.0))
+    del mpx
+    z = 0.7 * np.exp(2j * np.pi * dev * integral) + sigma / 0.577 * (noise(n, seed, offset) + 1j * noise(n, seed + 7, offset))
+    return quantise_u8iq(z)

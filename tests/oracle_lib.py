@@ -75,6 +75,7 @@ def lib():
             "orc_pll_free": (None, [vp]),
             "orc_pll_apply": (None, [vp, vp, sz, vp, vp]),
             "orc_pll_state": (None, [vp, vp, vp, vp]),
+            "orc_fm_stereo_decode": (None, [vp, vp, sz, vp]),
             "orc_freq_sweep": (sz, [f, f, i, f, f, vp, vp, sz]),
             "orc_src_new": (vp, [i, i, vp]),
             "orc_src_delete": (vp, [vp]),
@@ -271,6 +272,13 @@ class Pll:
         locked = np.empty(x.size, np.uint8)
         lib().orc_pll_apply(self.h, _p(x), x.size, _p(out), _p(locked))
         return out, locked
+
+    def stereo_decode(self, v):
+        """the (mono, diff) closure of src/main.rs:62-71 around this (pilot) Pll"""
+        v = np.ascontiguousarray(v, np.float32)
+        out = np.empty((v.size, 2), np.float32)
+        lib().orc_fm_stereo_decode(self.h, _p(v), v.size, _p(out))
+        return out
 
     def state(self):
         a, b, c = C.c_float(), C.c_float(), C.c_float()

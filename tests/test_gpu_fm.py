@@ -1,0 +1,130 @@
+"""FM broadcast stereo receiver: the chain of src/main.rs:32-81 on the device against
+the same chain assembled from the CPU oracle's parts."""
+import numpy as np
+import pytest
+
+import gen
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+RATE = 1.8e6
+
+
+def _pilot_design(sdr_or_oracle_is_oracle):
+    if sdr_or_oracle_is_oracle:
+        return O.pll_design(19000.0, 0.0002, (O.BQ_LOWPASS, 200.0, 0.7), (O.BQ_LOWPASS, 20.0, 0.7),
+                            (O.BQ_LOWPASS, 20.0, 0.7))
+    raise AssertionError
+
+
+def _oracle_chain(iq):
+    """src/main.rs:41-80 stage by stage with the oracle's operators; returns every intermediate"""
+    x = O.unpack_u8iq(iq)
+    demod = O.Pll(O.pll_design(0.0, 0.035, (O.BQ_LOWPASS, 80000.0, 0.7), (O.BQ_IDENTITY, 0.0, 0.0),
+                               (O.BQ_LOWPASS, 20000.0, 0.7)), np.float32(RATE))
+    out, locked = demod.apply(x)
+    v1 = (np.where(locked != 0, out, np.float32(0.0)).astype(np.float32) / np.float32(75000.0)).astype(np.float32)
+    r1 = float(np.float32(144000.0)) / float(np.float32(RATE))
+    v2 = O.resample_signal(v1, 2, r1)                      # SincFastest, main.rs:50
+    pilot = O.Pll(_pilot_design(True), np.float32(144000.0))
+    md = pilot.stereo_decode(v2)                           # main.rs:62-71
+    r2 = float(np.float32(48000.0)) / float(np.float32(144000.0))
+    md2 = O.resample_signal(md.view(np.complex64).ravel(), 0, r2)  # SincBestQuality, 2 channels, main.rs:73
+    d = np.float32(1.0) / (np.float32(75.0) * np.float32(0.001) * np.float32(0.001))
+    mono = O.biquad_apply(O.BQ_LR, d, 0.0, np.float32(48000.0), md2.real.copy())
+    diff = O.biquad_apply(O.BQ_LR, d, 0.0, np.float32(48000.0), md2.imag.copy())
+    lr = np.stack([mono + diff, mono - diff], axis=1).astype(np.float32)
+    return dict(v1=v1, v2=v2, md=md, md2=md2, lr=lr)
+
+
+def test_pilot_stereo_decode_matches_oracle(sdr):
+    """sdr_pll_stereo_decode == the closure of main.rs:62-71 around the oracle's Pll.  mono is exact; diff follows the
+    PLL's parity bar (the recurrence amplifies last-ulp differences of atan2/sincos, see test_gpu_pll_resample.py)."""
+    n = 60000
+    t = np.arange(n) / 144000.0
+    audio = 0.3 * np.sin(2 * np.pi * 1000 * t)
+    v = (0.5 * audio + 0.1 * np.sin(2 * np.pi * 19000 * t) +
+         0.3 * np.sin(2 * np.pi * 700 * t) * np.sin(2 * np.pi * 38000 * t)).astype(np.float32)
+    v += (0.01 * gen.noise(n, 77)).astype(np.float32)
+    want = O.Pll(_pilot_design(True), np.float32(144000.0)).stereo_decode(v)
+    des = sdr.PllDesign(19000.0, 0.0002, sdr.BiquadD.LowPass(200.0, 0.7), sdr.BiquadD.LowPass(20.0, 0.7),
+                        sdr.BiquadD.LowPass(20.0, 0.7))
+    p = sdr.PllBatch([des], 1, 144000.0)
+    got = p.stereo_decode(v)
+    assert got.shape == want.shape == (n, 2)
+    assert np.array_equal(got[:, 0].view(np.uint32), want[:, 0].view(np.uint32))  # mono = v * 0.5
+    # lock decisions agree except near the threshold crossing, and where both are locked diff agrees closely
+    both = (got[:, 1] != 0) & (want[:, 1] != 0)
+    assert ((got[:, 1] != 0) != (want[:, 1] != 0)).mean() < 1e-3
+    assert both.mean() > 0.3, "the pilot PLL never locked: the test signal is wrong"
+    err = np.abs(got[both, 1] - want[both, 1])
+    assert np.median(err) < 1e-5 and (err < 1e-3).mean() >= 0.99
+    # two streams, chunked: equals the single call bit for bit
+    p2 = sdr.PllBatch([des], 2, 144000.0)
+    vv = np.stack([v, v[::-1].copy()])
+    a = p2.stereo_decode(vv[:, :25000])
+    b = p2.stereo_decode(vv[:, 25000:])
+    cat = np.concatenate([a, b], axis=1)
+    assert np.array_equal(cat[0].view(np.uint32), got.view(np.uint32))
+
+
+@pytest.mark.parametrize("n_stations", [1, 3])
+def test_fm_stereo_chain_matches_oracle_chain(sdr, n_stations):
+    n = 360000  # 0.2 s at 1.8 MS/s
+    tones = [(1000.0, 2500.0), (440.0, 3000.0), (700.0, 5000.0)][:n_stations]
+    iq = np.stack([gen.fm_stereo_u8(n, RATE, fl, fr, 31 + i) for i, (fl, fr) in enumerate(tones)])
+    fm = sdr.FmStereo(n_stations, RATE)
+    assert fm.output_rate == 48000.0
+    got = fm.process(iq if n_stations > 1 else iq[0], end_of_input=True)
+    got = got.reshape(n_stations, -1, 2)
+    for i in range(n_stations):
+        ref = _oracle_chain(iq[i])
+        want = ref["lr"]
+        assert got[i].shape == want.shape, (got[i].shape, want.shape)
+        assert want.shape[0] in range(9590, 9610)  # 0.2 s at 48 kHz
+        err = np.abs(got[i] - want)
+        scale = max(1e-3, float(np.abs(want).max()))
+        # the demodulated audio must agree; the two PLLs carry the parity bar of the PLL tests
+        assert np.median(err) < 1e-5 * scale + 1e-7
+        assert (err < 2e-3 * scale).mean() >= 0.99, (float(err.max()), scale)
+
+
+def test_fm_stereo_streaming_calls_equal_one_call(sdr):
+    n = 200000
+    iq = gen.fm_stereo_u8(n, RATE, 1000.0, 3000.0, 5)
+    one = sdr.FmStereo(1, RATE).process(iq, end_of_input=True)
+    fm = sdr.FmStereo(1, RATE)
+    parts = []
+    pos = 0
+    for blk in (50001, 4096, 99999, 45904):
+        parts.append(fm.process(iq[2 * pos:2 * (pos + blk)], end_of_input=(pos + blk == n)))
+        pos += blk
+    assert pos == n
+    cat = np.concatenate(parts)
+    assert cat.shape == one.shape
+    # PLL / biquad state is carried exactly; the sinc converters agree up to the final f32 rounding across chunkings
+    assert np.abs(cat - one).max() <= 2e-6 * max(1.0, float(np.abs(one).max()))
+    fm.reset()
+    again = fm.process(iq, end_of_input=True)
+    assert np.array_equal(again.view(np.uint32), one.view(np.uint32))
+
+
+def test_fm_stereo_separates_left_and_right(sdr):
+    """End-to-end sanity on physics rather than on the oracle: once the pilot PLL has locked, a tone sent on the left
+    channel only comes out on the left."""
+    n = 900000  # 0.5 s
+    iq = gen.fm_stereo_u8(n, RATE, 1000.0, 3000.0, 9, sigma=0.002)
+    lr = sdr.FmStereo(1, RATE).process(iq, end_of_input=True)
+    tail = lr[-4800:]  # last 0.1 s
+    t = np.arange(tail.shape[0]) / 48000.0
+
+    def amp(x, f):
+        return 2 * abs(np.mean(x * np.exp(-2j * np.pi * f * t)))
+    l1, l3 = amp(tail[:, 0], 1000.0), amp(tail[:, 0], 3000.0)
+    r1, r3 = amp(tail[:, 1], 1000.0), amp(tail[:, 1], 3000.0)
+    print("left: 1k %.4f 3k %.4f   right: 1k %.4f 3k %.4f" % (l1, l3, r1, r3))
+    assert l1 > 0.05 and r3 > 0.02
+    # measured 8.7x and 3.6x: the reference's decode (v / nco^2 with the loop's static phase error, no pre-emphasis
+    # in the generator) separates the channels without being a hi-fi decoder
+    assert l1 > 3 * l3 and r3 > 3 * r1

@@ -49,3 +49,58 @@ def test_sharded_fir_equals_single_stream_on_oracle(sdr):
         f.apply(x[hlo:lo])  # prime with the halo
         parts.append(f.apply(x[lo:hi])[9::10])
     assert np.array_equal(np.concatenate(parts), whole)
+
+
+def test_rtltcp_wire_protocol_against_a_loopback_server(sdr):
+    """src/rtltcp.rs:60-134 on the wire: 12-byte greeting, then SetSampleRate, SetFrequency, gain mode (+ gain),
+    SetRtlAgc as 1 + 4 big-endian bytes each, then raw I/Q bytes until the peer closes."""
+    import socket
+    import threading
+    R = sdr.rtltcp
+    assert R.command_bytes(R.CMD_SET_FREQUENCY, 100000000) == bytes([0x01, 0x05, 0xF5, 0xE1, 0x00])
+    assert R.command_bytes(R.CMD_SET_RTL_AGC, 1) == bytes([0x08, 0, 0, 0, 1])
+    assert R.gain_tenths_db(49.6) == 496 and R.gain_tenths_db(-3.0) == 0 and R.gain_tenths_db(0.25) == 3
+    for bad in (225000, 300001, 900000, 3200001):
+        try:
+            R.check_sample_rate(bad)
+            raise AssertionError("accepted %d" % bad)
+        except ValueError:
+            pass
+    for ok in (225001, 300000, 900001, 1800000, 2400000, 3200000):
+        R.check_sample_rate(ok)
+
+    payload = gen.random_u8(2 * 5000 + 1, 77)  # odd length: the dangling byte is dropped (read error on Q, :138-139)
+    srv = socket.socket()
+    srv.bind(("127.0.0.1", 0))
+    srv.listen(1)
+    port = srv.getsockname()[1]
+    seen = {}
+
+    def serve():
+        c, _ = srv.accept()
+        c.sendall(b"RTL0" + bytes([0, 0, 0, 5, 0, 0, 0, 29]))
+        buf = b""
+        want = 5 * 5  # manual gain: rate, freq, gain mode, gain, agc
+        while len(buf) < want:
+            b = c.recv(want - len(buf))
+            if not b:
+                break
+            buf += b
+        seen["cmds"] = buf
+        c.sendall(payload.tobytes())
+        c.close()
+
+    t = threading.Thread(target=serve, daemon=True)
+    t.start()
+    sig = R.RtlTcp().address("127.0.0.1:%d" % port).rate(2400000).frequency(99500000).gain(20.7).rtlagc(True).listen(timeout=10)
+    assert sig.conn.id == b"RTL0" + bytes([0, 0, 0, 5, 0, 0, 0, 29])
+    assert sig.rate() == np.float32(2400000.0)
+    got = [sig.next_raw(1234) for _ in range(6)]
+    t.join(10)
+    srv.close()
+    raw = np.concatenate(got)
+    assert np.array_equal(raw, payload[:10000]) and len(sig.next_raw(16)) == 0
+    import struct
+    assert seen["cmds"] == b"".join(struct.pack(">BI", c, a) for c, a in
+                                    [(2, 2400000), (1, 99500000), (3, 1), (4, 207), (8, 1)])
+    sig.conn.close()

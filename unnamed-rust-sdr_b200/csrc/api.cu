@@ -824,6 +824,42 @@ extern "C" int sdr_pll_process(sdr_pll_t *p, const float *in, size_t n, size_t i
     return cuda_status(cudaStreamSynchronize(st));
 }
 
+extern "C" int sdr_pll_stereo_decode_dev(sdr_pll_t *p, const float *v, size_t n, size_t in_stride, float *out_md,
+                                         size_t out_stride) {
+    if (!p) return SDR_ERR_NULL_HANDLE;
+    if (n == 0) return SDR_OK;
+    if (!v || !out_md) return SDR_ERR_BAD_DATA_PTR;
+    if (p->n_streams == 1) { in_stride = n; out_stride = n; }
+    if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
+    DeviceGuard g(p->dev);
+    return pll_stereo_launch(v, (long long)n, (long long)in_stride, out_md, (long long)out_stride, p->d_params,
+                             p->n_designs == 1, p->d_state, (int)p->n_streams, (p->flags & SDR_PLL_FAST_MATH) != 0,
+                             p->stream.s);
+}
+
+extern "C" int sdr_pll_stereo_decode(sdr_pll_t *p, const float *v, size_t n, size_t in_stride, float *out_md,
+                                     size_t out_stride) {
+    if (!p) return SDR_ERR_NULL_HANDLE;
+    if (n == 0) return SDR_OK;
+    if (!v || !out_md) return SDR_ERR_BAD_DATA_PTR;
+    if (p->n_streams == 1) { in_stride = n; out_stride = n; }
+    if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
+    DeviceGuard g(p->dev);
+    const size_t S = p->n_streams;
+    int rc = p->d_in.reserve(S * n * 4);
+    if (!rc) rc = p->d_out.reserve(S * n * 8);
+    if (rc) return rc;
+    cudaStream_t st = p->stream.s;
+    rc = copy2d(p->d_in.p, n * 4, v, in_stride * 4, n * 4, S, cudaMemcpyHostToDevice, st);
+    if (rc) return rc;
+    rc = pll_stereo_launch((const float *)p->d_in.p, (long long)n, (long long)n, (float *)p->d_out.p, (long long)n,
+                           p->d_params, p->n_designs == 1, p->d_state, (int)S, (p->flags & SDR_PLL_FAST_MATH) != 0, st);
+    if (rc) return rc;
+    rc = copy2d(out_md, out_stride * 8, p->d_out.p, n * 8, n * 8, S, cudaMemcpyDeviceToHost, st);
+    if (rc) return rc;
+    return cuda_status(cudaStreamSynchronize(st));
+}
+
 extern "C" int sdr_pll_get_state(sdr_pll_t *p, size_t idx, float *nphase, float *vre, float *vim) {
     if (!p) return SDR_ERR_NULL_HANDLE;
     if (idx >= p->n_streams) return SDR_ERR_INVALID_ARG;

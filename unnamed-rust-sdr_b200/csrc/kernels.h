@@ -91,6 +91,13 @@ int pll_launch(const float2 *in, long long n, long long in_stride, float *out, u
                int n_streams, bool fast_math, bool any_identity, cudaStream_t st);
 
 // stand-alone biquad stream filter: n_seq real sequences (a complex stream is two), element i of sequence s at
+// FM stereo pieces (src/main.rs:49,62-71,76-80): pilot Pll + (mono, diff) decode, demodulator output map, L/R matrix
+int pll_stereo_launch(const float *in, long long n, long long in_stride, float *out_md, long long out_stride,
+                      const PllParams *params, int params_shared, PllState *state, int n_streams, bool fast_math,
+                      cudaStream_t st);
+int fm_demod_map_launch(const float *v, const uint8_t *locked, float *out, long long n, cudaStream_t st);
+int fm_matrix_launch(const float *md, long long md_stride, float *lr, long long lr_stride, int rows, long long n_frames,
+                     cudaStream_t st);
 // in[(s / W) * in_stride * W + i * W + s % W], W = 1 (f32) or 2 (c64); coef / state: 5 / 4 floats per sequence
 int biquad_launch(const float *in, long long n, long long in_stride, float *out, long long out_stride, int W,
                   const float *coef, const int *kind, int coef_shared, float *state, int n_seq, cudaStream_t st);

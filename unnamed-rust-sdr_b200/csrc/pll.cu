@@ -319,7 +319,91 @@ __global__ void __launch_bounds__(32) biquad_kernel(const float *__restrict__ in
     if (live) { state[4 * my] = x1; state[4 * my + 1] = x2; state[4 * my + 2] = y1; state[4 * my + 3] = y2; }
 }
 
+// FM stereo decode around a pilot-tone Pll -- the closure of src/main.rs:62-71:
+//     mono = v * 0.5
+//     diff = Some(_) = pllpilot.apply(Complex::new(v, 0.0)) ? (v / pllpilot.value.powi(2)).re * 0.5 : 0.0
+// One lane per station; the whole recurrence (loop, lock and output filters) runs in the lane, the input is real.
+// powi(2) = z * z; f32 / Complex = (a*c/|z|^2, -a*d/|z|^2) (num-complex 0.2; the crate is not in the reference tree).
+// The rates here are 12.5x below the demodulator's (144 kS/s), so this kernel keeps the simple one-warp structure.
+template <bool FAST>
+__global__ void __launch_bounds__(32) pll_stereo_kernel(const float *__restrict__ in, long long n, long long in_stride,
+                                                        float2 *__restrict__ out, long long out_stride,
+                                                        const PllParams *__restrict__ params, int params_shared,
+                                                        PllState *__restrict__ state, int n_streams) {
+    const int my = blockIdx.x * 32 + threadIdx.x;
+    if (my >= n_streams) return;
+    const PllParams p = params[params_shared ? 0 : my];
+    PllState st = state[my];
+    const Biquad1 lf = make_bq(p.lc, p.lk), of = make_bq(p.oc, p.ok), kf = make_bq(p.kc, p.kk);
+    const float *x = in + (long long)my * in_stride;
+    float2 *y = out + (long long)my * out_stride;
+    float vn = n > 0 ? __ldg(x) : 0.f;
+    for (long long i = 0; i < n; ++i) {
+        const float v = vn;
+        if (i + 1 < n) vn = __ldg(x + i + 1);
+        const float2 m = pll_step<FAST, true>(p, lf, st, v, 0.0f);
+        const float lk = bq_apply<true>(kf, m.x, st.kx1, st.kx2, st.ky1, st.ky2);
+        (void)bq_apply<true>(of, __fmul_rn(m.y, p.rate), st.ox1, st.ox2, st.oy1, st.oy2);  // state only (pll.rs:79)
+        float diff = 0.0f;
+        if (lk > 0.01f) {
+            const float zr = __fsub_rn(__fmul_rn(st.vre, st.vre), __fmul_rn(st.vim, st.vim));
+            const float zi = __fadd_rn(__fmul_rn(st.vre, st.vim), __fmul_rn(st.vim, st.vre));
+            const float ns = __fadd_rn(__fmul_rn(zr, zr), __fmul_rn(zi, zi));
+            diff = __fmul_rn(__fdiv_rn(__fmul_rn(v, zr), ns), 0.5f);
+        }
+        y[i] = make_float2(__fmul_rn(v, 0.5f), diff);
+    }
+    state[my] = st;
+}
+
+// FM demodulator output map of src/main.rs:49: |f| f.unwrap_or(0.0) / 75000.0
+__global__ void fm_demod_map_kernel(const float *__restrict__ v, const uint8_t *__restrict__ locked, float *out,
+                                    long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __fdiv_rn(locked[i] ? v[i] : 0.0f, 75000.0f);
+}
+
+// final stereo matrix of src/main.rs:76-80 on de-emphasised (mono, diff) frames: (mono + diff, mono - diff);
+// blockIdx.y = station row
+__global__ void fm_matrix_kernel(const float2 *__restrict__ md, long long md_stride, float2 *__restrict__ lr,
+                                 long long lr_stride, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const float2 a = md[blockIdx.y * md_stride + i];
+        lr[blockIdx.y * lr_stride + i] = make_float2(__fadd_rn(a.x, a.y), __fsub_rn(a.x, a.y));
+    }
+}
+
 }  // namespace
+
+int pll_stereo_launch(const float *in, long long n, long long in_stride, float *out_md, long long out_stride,
+                      const PllParams *params, int params_shared, PllState *state, int n_streams, bool fast_math,
+                      cudaStream_t st) {
+    if (n <= 0 || n_streams <= 0) return SDR_OK;
+    const unsigned grid = (unsigned)((n_streams + 31) / 32);
+    if (fast_math)
+        pll_stereo_kernel<true><<<grid, 32, 0, st>>>(in, n, in_stride, (float2 *)out_md, out_stride, params, params_shared, state, n_streams);
+    else
+        pll_stereo_kernel<false><<<grid, 32, 0, st>>>(in, n, in_stride, (float2 *)out_md, out_stride, params, params_shared, state, n_streams);
+    count_launch();
+    return launch_status();
+}
+
+int fm_demod_map_launch(const float *v, const uint8_t *locked, float *out, long long n, cudaStream_t st) {
+    if (n <= 0) return SDR_OK;
+    fm_demod_map_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(v, locked, out, n);
+    count_launch();
+    return launch_status();
+}
+
+int fm_matrix_launch(const float *md, long long md_stride, float *lr, long long lr_stride, int rows, long long n_frames,
+                     cudaStream_t st) {
+    if (n_frames <= 0 || rows <= 0) return SDR_OK;
+    fm_matrix_kernel<<<dim3((unsigned)((n_frames + 255) / 256), (unsigned)rows), 256, 0, st>>>(
+        (const float2 *)md, md_stride, (float2 *)lr, lr_stride, n_frames);
+    count_launch();
+    return launch_status();
+}
 
 int biquad_launch(const float *in, long long n, long long in_stride, float *out, long long out_stride, int W,
                   const float *coef, const int *kind, int coef_shared, float *state, int n_seq, cudaStream_t st) {

@@ -262,6 +262,11 @@ class Pll {  // pll.rs:13-85 ; Output = Option<f32>
         process(&value, 1, o);
         return o[0];
     }
+    // the closure of main.rs:62-71 with this Pll as `pllpilot`: v -> (mono, diff)
+    void stereo_decode(const float *v, size_t n, std::vector<std::pair<float, float>> &out) {
+        out.resize(n);
+        check(sdr_pll_stereo_decode(h_, v, n, n, reinterpret_cast<float *>(out.data()), n), "Pll::stereo_decode");
+    }
     float nphase() { float a, b, c; check(sdr_pll_get_state(h_, 0, &a, &b, &c), "Pll::nphase"); return a; }  // pub nphase
     Complex value() { float a, b, c; check(sdr_pll_get_state(h_, 0, &a, &b, &c), "Pll::value"); return {b, c}; }  // pub value
 };
@@ -601,4 +606,44 @@ inline std::vector<std::pair<float, Complex>> rfft(signal::Sig<float> input) {
 }
 
 }  // namespace fft
+
+// =========================================================================================
+namespace app {
+
+// The receiver of src/main.rs:32-81 as one device-resident pipeline (sdr_fm_*): rtl_tcp bytes in, 48 kHz
+// (left, right) frames out; a batch of stations shares every launch.
+class FmStereo {
+    sdr_fm_t *h_ = nullptr;
+    size_t n_st_;
+
+  public:
+    explicit FmStereo(size_t n_stations = 1, float rate = 1800000.0f, unsigned flags = 0) : n_st_(n_stations) {
+        sdr_fm_config_t cfg{};
+        cfg.n_stations = n_stations;
+        cfg.rate = rate;
+        cfg.flags = flags;
+        int err = 0;
+        h_ = sdr_fm_create(&cfg, &err);
+        if (!h_) throw Error(err, "FmStereo::new");
+    }
+    FmStereo(const FmStereo &) = delete;
+    FmStereo &operator=(const FmStereo &) = delete;
+    ~FmStereo() { sdr_fm_destroy(h_); }
+    float rate() const { return sdr_fm_output_rate(h_); }
+    // iq: n_stations rows of 2n bytes; out: n_stations rows of the returned number of frames
+    size_t process(const uint8_t *iq, size_t n, bool end_of_input, std::vector<std::pair<float, float>> &out) {
+        const size_t cap = sdr_fm_max_output(h_, n);
+        out.resize(n_st_ * cap);
+        size_t got = 0;
+        check(sdr_fm_process(h_, iq, n, 2 * n, reinterpret_cast<float *>(out.data()), cap, cap, &got, end_of_input ? 1 : 0),
+              "FmStereo::process");
+        if (got != cap)
+            for (size_t s = 1; s < n_st_; ++s) std::copy(out.begin() + s * cap, out.begin() + s * cap + got, out.begin() + s * got);
+        out.resize(n_st_ * got);
+        return got;
+    }
+    void reset() { check(sdr_fm_reset(h_), "FmStereo::reset"); }
+};
+
+}  // namespace app
 }  // namespace sdr

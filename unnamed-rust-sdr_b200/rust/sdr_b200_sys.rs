@@ -20,6 +20,8 @@ pub enum sdr_fir_t {}
 pub enum sdr_fft_t {}
 pub enum sdr_pll_t {}
 pub enum sdr_biquad_t {}
+pub enum sdr_fm_t {}
+pub enum sdr_window_fft_t {}
 pub enum sdr_channelizer_t {}
 /// same role as libsamplerate's SRC_STATE (src/resample.rs:12)
 pub enum SDR_SRC_STATE {}
@@ -86,6 +88,26 @@ pub struct sdr_biquad_config_t {
     pub stream: *mut c_void,
 }
 
+#[repr(C)]
+pub struct sdr_window_fft_config_t {
+    pub window: size_t,
+    pub hop: size_t,
+    pub input_format: c_int,
+    pub flags: c_uint,
+    pub device: c_int,
+    pub stream: *mut c_void,
+}
+
+#[repr(C)]
+pub struct sdr_fm_config_t {
+    pub n_stations: size_t,
+    pub rate: c_float,
+    pub pilot: c_float,
+    pub flags: c_uint,
+    pub device: c_int,
+    pub stream: *mut c_void,
+}
+
 /// identical layout to libsamplerate's SRC_DATA as built at src/resample.rs:49-58
 #[repr(C)]
 pub struct SDR_SRC_DATA {
@@ -136,6 +158,26 @@ extern "C" {
     pub fn sdr_biquad_clone(b: *const sdr_biquad_t, err: *mut c_int) -> *mut sdr_biquad_t;
     pub fn sdr_biquad_process(b: *mut sdr_biquad_t, input: *const c_float, n: size_t, in_stride: size_t,
                               output: *mut c_float, out_stride: size_t) -> c_int;
+
+    // src/main.rs:62-71 (pilot Pll + stereo decode) and src/main.rs:32-81 (the whole FM stereo receiver)
+    pub fn sdr_pll_stereo_decode(p: *mut sdr_pll_t, v: *const c_float, n: size_t, in_stride: size_t,
+                                 out_mono_diff: *mut c_float, out_stride: size_t) -> c_int;
+    pub fn sdr_fm_create(cfg: *const sdr_fm_config_t, err: *mut c_int) -> *mut sdr_fm_t;
+    pub fn sdr_fm_destroy(f: *mut sdr_fm_t);
+    pub fn sdr_fm_reset(f: *mut sdr_fm_t) -> c_int;
+    pub fn sdr_fm_output_rate(f: *const sdr_fm_t) -> c_float;
+    pub fn sdr_fm_max_output(f: *const sdr_fm_t, n: size_t) -> size_t;
+    pub fn sdr_fm_process(f: *mut sdr_fm_t, iq: *const u8, n: size_t, in_stride: size_t, out: *mut c_float,
+                          out_cap: size_t, out_stride: size_t, n_out: *mut size_t, end_of_input: c_int) -> c_int;
+
+    // examples/live.rs:30-39: window(duration).decimate(fps).map(fft::fft)
+    pub fn sdr_window_fft_create(cfg: *const sdr_window_fft_config_t, err: *mut c_int) -> *mut sdr_window_fft_t;
+    pub fn sdr_window_fft_destroy(h: *mut sdr_window_fft_t);
+    pub fn sdr_window_fft_reset(h: *mut sdr_window_fft_t) -> c_int;
+    pub fn sdr_window_fft_size(h: *const sdr_window_fft_t) -> size_t;
+    pub fn sdr_window_fft_output_count(h: *const sdr_window_fft_t, n_in: size_t) -> size_t;
+    pub fn sdr_window_fft_process(h: *mut sdr_window_fft_t, input: *const c_void, n_in: size_t, out_c64: *mut c_float,
+                                  out_cap: size_t, n_windows: *mut size_t) -> c_int;
 
     // drop-in for libsamplerate_sys::{src_new, src_process, ...} used by src/resample.rs
     pub fn sdr_src_new(converter_type: c_int, channels: c_int, error: *mut c_int) -> *mut SDR_SRC_STATE;

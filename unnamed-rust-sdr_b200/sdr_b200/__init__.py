@@ -4,10 +4,10 @@ sample-stream hot path of agrif/unnamed-rust-sdr.  Module layout follows the ref
 the built CUDA library or without a CUDA device raises."""
 from . import _ffi
 from ._ffi import (FMT_C64, FMT_F32, FMT_U8IQ, LIB_PATH, PROTOTYPES, SdrError, lib)
-from .ops import (Biquad, BiquadD, Channelizer, ConverterType, FftPlan, Fir, Identity, PllBatch, PllDesign,
-                  ResampleError, SampleRate, Timer, block_samples, decimate_wait, device_count,
+from .ops import (Biquad, BiquadD, Channelizer, ConverterType, FftPlan, Fir, FmStereo, Identity, PllBatch, PllDesign,
+                  ResampleError, SampleRate, Timer, WindowFft, block_samples, decimate_wait, device_count,
                   device_info, duration_samples, fft, fft_labels, kernel_launch_count, rfft, sinc_table,
                   unpack_u8iq)
-from . import shard, signal
+from . import rtltcp, shard, signal
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -44,6 +44,15 @@ class BiquadConfig(C.Structure):
                 ("sample_complex", i32), ("device", i32), ("stream", vp)]
 
 
+class FmConfig(C.Structure):
+    _fields_ = [("n_stations", sz), ("rate", f32), ("pilot", f32), ("flags", C.c_uint), ("device", i32),
+                ("stream", vp)]
+
+
+class WindowFftConfig(C.Structure):
+    _fields_ = [("window", sz), ("hop", sz), ("input_format", i32), ("flags", C.c_uint), ("device", i32), ("stream", vp)]
+
+
 class SrcData(C.Structure):
     _fields_ = [("data_in", vp), ("data_out", vp), ("input_frames", C.c_long), ("output_frames", C.c_long),
                 ("input_frames_used", C.c_long), ("output_frames_gen", C.c_long),
@@ -82,7 +91,23 @@ PROTOTYPES = {
     "sdr_pll_clone": (vp, [vp, C.POINTER(i32)]),
     "sdr_pll_process": (i32, [vp, vp, sz, sz, vp, vp, sz]),
     "sdr_pll_process_dev": (i32, [vp, vp, sz, sz, vp, vp, sz]),
+    "sdr_pll_stereo_decode": (i32, [vp, vp, sz, sz, vp, sz]),
+    "sdr_pll_stereo_decode_dev": (i32, [vp, vp, sz, sz, vp, sz]),
     "sdr_pll_get_state": (i32, [vp, sz, C.POINTER(f32), C.POINTER(f32), C.POINTER(f32)]),
+    "sdr_window_fft_create": (vp, [C.POINTER(WindowFftConfig), C.POINTER(i32)]),
+    "sdr_window_fft_destroy": (None, [vp]),
+    "sdr_window_fft_reset": (i32, [vp]),
+    "sdr_window_fft_size": (sz, [vp]),
+    "sdr_window_fft_output_count": (sz, [vp, sz]),
+    "sdr_window_fft_process": (i32, [vp, vp, sz, vp, sz, C.POINTER(sz)]),
+    "sdr_window_fft_process_dev": (i32, [vp, vp, sz, vp, sz, C.POINTER(sz)]),
+    "sdr_fm_create": (vp, [C.POINTER(FmConfig), C.POINTER(i32)]),
+    "sdr_fm_destroy": (None, [vp]),
+    "sdr_fm_reset": (i32, [vp]),
+    "sdr_fm_output_rate": (f32, [vp]),
+    "sdr_fm_max_output": (sz, [vp, sz]),
+    "sdr_fm_process": (i32, [vp, vp, sz, sz, vp, sz, sz, C.POINTER(sz), i32]),
+    "sdr_fm_process_dev": (i32, [vp, vp, sz, sz, vp, sz, sz, C.POINTER(sz), i32]),
     "sdr_biquad_create": (vp, [C.POINTER(BiquadConfig), C.POINTER(i32)]),
     "sdr_biquad_destroy": (None, [vp]),
     "sdr_biquad_reset": (i32, [vp]),

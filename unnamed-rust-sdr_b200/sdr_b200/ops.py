@@ -345,6 +345,20 @@ class PllBatch:
         check(lib().sdr_pll_process_dev(self.h, _ptr(d_in), n, in_stride or n, _ptr(d_out), _ptr(d_locked),
                                         out_stride or n), "sdr_pll_process_dev")
 
+    def stereo_decode(self, v):
+        """the (mono, diff) closure of src/main.rs:62-71 around this (pilot) Pll: v f32 [n] or [n_streams, n] ->
+        float32 [..., n, 2]"""
+        v = np.ascontiguousarray(v, np.float32)
+        rows = v.reshape(self.n_streams, -1)
+        n = rows.shape[1]
+        out = np.empty((self.n_streams, n, 2), np.float32)
+        check(lib().sdr_pll_stereo_decode(self.h, rows.ctypes.data, n, n, out.ctypes.data, n), "sdr_pll_stereo_decode")
+        return out[0] if v.ndim <= 1 else out
+
+    def stereo_decode_dev(self, d_v, n, d_out, in_stride=None, out_stride=None):
+        check(lib().sdr_pll_stereo_decode_dev(self.h, _ptr(d_v), n, in_stride or n, _ptr(d_out), out_stride or n),
+              "sdr_pll_stereo_decode_dev")
+
     def state(self, idx=0):
         a, b, c = C.c_float(), C.c_float(), C.c_float()
         check(lib().sdr_pll_get_state(self.h, idx, C.byref(a), C.byref(b), C.byref(c)), "sdr_pll_get_state")
@@ -363,6 +377,105 @@ class PllBatch:
     def close(self):
         if getattr(self, "h", None):
             lib().sdr_pll_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class WindowFft:
+    """signal.window(duration).decimate(fps).map(fft::fft) of examples/live.rs:30-39: one spectrum per kept sliding
+    window.  window = duration_samples(rate, duration), hop = decimate_wait(rate, fps)."""
+
+    def __init__(self, window, hop, fmt="c64", shift=True, norm=True, device=0, stream=None):
+        self.fmt = {"u8iq": F.FMT_U8IQ, "c64": F.FMT_C64}[fmt]
+        flags = (F.FFT_SHIFT if shift else 0) | (F.FFT_NORM if norm else 0)
+        cfg = F.WindowFftConfig(int(window), int(hop), self.fmt, flags, device, _stream_ptr(stream))
+        err = C.c_int(0)
+        self.h = lib().sdr_window_fft_create(C.byref(cfg), C.byref(err))
+        if not self.h:
+            raise SdrError(err.value, "sdr_window_fft_create")
+        self.window = int(window)
+
+    def output_count(self, n_in):
+        return lib().sdr_window_fft_output_count(self.h, n_in)
+
+    def process(self, x):
+        """x: uint8 [2n] (u8iq) or complex64 [n] -> complex64 [n_windows, window]"""
+        if self.fmt == F.FMT_U8IQ:
+            x = np.ascontiguousarray(x, np.uint8)
+            n = x.size // 2
+        else:
+            x = np.ascontiguousarray(x, np.complex64)
+            n = x.size
+        nw = self.output_count(n)
+        out = np.empty((max(nw, 1), self.window), np.complex64)
+        got = C.c_size_t(0)
+        check(lib().sdr_window_fft_process(self.h, x.ctypes.data if n else None, n, out.ctypes.data, max(nw, 1),
+                                           C.byref(got)), "sdr_window_fft_process")
+        return out[:got.value]
+
+    def process_dev(self, d_in, n, d_out, out_cap):
+        got = C.c_size_t(0)
+        check(lib().sdr_window_fft_process_dev(self.h, _ptr(d_in), n, _ptr(d_out), out_cap, C.byref(got)),
+              "sdr_window_fft_process_dev")
+        return got.value
+
+    def reset(self):
+        check(lib().sdr_window_fft_reset(self.h), "sdr_window_fft_reset")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sdr_window_fft_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+
+class FmStereo:
+    """The FM broadcast stereo receiver of src/main.rs:32-81 for a batch of stations, device-resident end to end:
+    u8 IQ -> Pll demodulator -> /75000 -> SincFastest to 144 kHz -> pilot Pll + (mono, diff) -> SincBest to 48 kHz ->
+    Lr de-emphasis -> (left, right)."""
+
+    def __init__(self, n_stations=1, rate=1.8e6, pilot=0.0, fast_math=False, device=0, stream=None):
+        self.n_stations = int(n_stations)
+        cfg = F.FmConfig(self.n_stations, rate, pilot, F.PLL_FAST_MATH if fast_math else 0, device, _stream_ptr(stream))
+        err = C.c_int(0)
+        self.h = lib().sdr_fm_create(C.byref(cfg), C.byref(err))
+        if not self.h:
+            raise SdrError(err.value, "sdr_fm_create")
+
+    @property
+    def output_rate(self):
+        return lib().sdr_fm_output_rate(self.h)
+
+    def max_output(self, n):
+        return lib().sdr_fm_max_output(self.h, n)
+
+    def process(self, iq, end_of_input=False):
+        """iq: uint8 [2n] or [n_stations, 2n] -> float32 [n_out, 2] or [n_stations, n_out, 2] (left, right) at 48 kHz"""
+        iq = np.ascontiguousarray(iq, np.uint8)
+        rows = iq.reshape(self.n_stations, -1)
+        n = rows.shape[1] // 2
+        cap = self.max_output(n)
+        out = np.empty((self.n_stations, cap, 2), np.float32)
+        got = C.c_size_t(0)
+        check(lib().sdr_fm_process(self.h, rows.ctypes.data, n, rows.shape[1], out.ctypes.data, cap, cap,
+                                   C.byref(got), int(bool(end_of_input))), "sdr_fm_process")
+        out = out[:, :got.value]
+        return out[0] if iq.ndim <= 1 else out
+
+    def process_dev(self, d_iq, n, in_stride, d_out, out_cap, out_stride=None, end_of_input=False):
+        got = C.c_size_t(0)
+        check(lib().sdr_fm_process_dev(self.h, _ptr(d_iq), n, in_stride, _ptr(d_out), out_cap, out_stride or out_cap,
+                                       C.byref(got), int(bool(end_of_input))), "sdr_fm_process_dev")
+        return got.value
+
+    def reset(self):
+        check(lib().sdr_fm_reset(self.h), "sdr_fm_reset")
+
+    def close(self):
+        if getattr(self, "h", None):
+            lib().sdr_fm_destroy(self.h)
             self.h = None
 
     __del__ = close

@@ -353,3 +353,25 @@ def fft(signal):
 def rfft(signal):
     """fft::rfft(signal) (src/fft.rs:30-37)."""
     return ops.rfft(signal.collect(), float(signal.rate()))
+
+
+def window_spectra(signal, duration, fps, block=DEFAULT_BLOCK):
+    """signal.window(duration).decimate(fps).map(|w| fft::fft(w)) of examples/live.rs:30-39 as a generator of
+    (labels, spectra[n_windows, window]) per input block.  window = round(duration * rate) (adapters/mod.rs:279),
+    hop = Decimate's wait (mod.rs:22).  Raw u8 IQ sources are unpacked on the device."""
+    rate = float(signal.rate())
+    window = ops.duration_samples(rate, duration)
+    hop = ops.decimate_wait(rate, fps)
+    raw = hasattr(signal, "next_raw")
+    wf = ops.WindowFft(window, hop, "u8iq" if raw else "c64")
+    labels = ops.fft_labels(window, rate)
+    try:
+        while True:
+            b = signal.next_raw(block) if raw else signal.next_block(block)
+            if len(b) == 0:
+                return
+            s = wf.process(b)
+            if len(s):
+                yield labels, s
+    finally:
+        wf.close()
