@@ -64,6 +64,17 @@ __device__ __forceinline__ T div_t(T num, T den) {
     return fma_t(fma_t(-den, q, num), r, q);
 }
 
+// f64 quotient for the atan2 below, 0 < den < 1e300 (f32 magnitudes widened to f64: no rescaling needed): the
+// 20-bit hardware seed (MUFU.RCP64H, no f32 round trip) and ONE Newton step give 2^-40 -- the result is rounded to f32
+// afterwards, a correctly rounded f64 division would buy nothing.  Depth: MUFU + 2 DFMA + DMUL (was 3 F2F + MUFU + 7).
+__device__ __forceinline__ double div_fast64(double num, double den) {
+    double r0;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r0) : "d"(den));
+    const double e = __fma_rn(-den, r0, 1.0);
+    const double r1 = __fma_rn(r0, e, r0);
+    return num * r1;
+}
+
 // atan(t) = t + t * z * A(z), z = t^2 <= tan^2(pi/8): Taylor coefficients (-1)^k / (2k+1), NT terms, Estrin
 template <typename T, int NT>
 __device__ __forceinline__ T atan_poly(T z) {
@@ -83,7 +94,7 @@ __device__ __forceinline__ T atan_poly(T z) {
 }
 
 template <typename T>
-__device__ __forceinline__ T atan2_t(float yf, float xf) {
+__device__ __forceinline__ T atan2_generic(float yf, float xf) {
     const T x = (T)xf, y = (T)yf;
     const T ax = fabs(x), ay = fabs(y);
     const T mx = fmax(ax, ay), mn = fmin(ax, ay);
@@ -99,6 +110,47 @@ __device__ __forceinline__ T atan2_t(float yf, float xf) {
     return (__float_as_int(yf) < 0) ? -r : r;
 }
 
+// The f64 routine on the PLL's dependent chain, arranged for DEPTH (a dependent DFMA costs ~18 cycles here):
+//   * the same octant reduction, but the three fix-ups (pi/4 + r, pi/2 - r, pi - r, -r) are folded into ONE
+//     fma(S, r, C): S = +-1 and C come from the operand signs and magnitudes, off the chain;
+//   * division by seed + one Newton step (div_fast64);
+//   * atan(t) = t + t z A(z) with an 8-term near-minimax A on z <= tan^2(pi/8) (Chebyshev-node fit, relative error
+//     1.1e-13 -- the f32 result is still the correctly rounded one except for ~2e-6 of the arguments), Estrin in 3 levels
+//     instead of the 14-term Taylor polynomial's 4.
+__device__ __forceinline__ double atan2_f64(float yf, float xf) {
+    // magnitudes ordered in f32 (one FMNMX each; widening is exact and monotone, so the f64 values are the same)
+    const float axf = fabsf(xf), ayf = fabsf(yf);
+    const float mxf = fmaxf(axf, ayf), mnf = fminf(axf, ayf);
+    const double mx = (double)mxf, mn = (double)mnf;
+    // which side of tan(pi/8) is decided in f32 too: an argument within an ulp of the boundary may take either branch,
+    // both are accurate there (the polynomial's error stays below 2e-13 for z up to 0.1716 * (1 + 1e-6))
+    const bool red = mnf > 0.41421357f * mxf;
+    const bool swap = ayf > axf, xneg = __float_as_int(xf) < 0, yneg = __float_as_int(yf) < 0;
+    double C = red ? 0.78539816339744831 : 0.0, S = 1.0;
+    if (swap) { C = 1.5707963267948966 - C; S = -S; }
+    if (xneg) { C = 3.1415926535897932 - C; S = -S; }
+    if (yneg) { C = -C; S = -S; }
+    const double num = red ? mn - mx : mn;
+    const double den = red ? mn + mx : mx;
+    const bool ok = den > 0.0 && den < 1e300;  // 0/0 -> 0 as before; inf or NaN operands must not poison the loop
+    const double t = ok ? div_fast64(num, den) : 0.0;
+    const double z = t * t, z2 = z * z, z4 = z2 * z2, tz = t * z;
+    const double a0 = -0.33333333333266202, a1 = 0.19999999949854971, a2 = -0.14285708110368922,
+                 a3 = 0.11110819716945537, a4 = -0.090841018978842836, a5 = 0.076048000638505017,
+                 a6 = -0.060273075254674978, a7 = 0.032956796366944874;
+    const double p0 = __fma_rn(a1, z, a0), p1 = __fma_rn(a3, z, a2), p2 = __fma_rn(a5, z, a4), p3 = __fma_rn(a7, z, a6);
+    const double q0 = __fma_rn(p1, z2, p0), q1 = __fma_rn(p3, z2, p2);
+    const double A = __fma_rn(q1, z4, q0);
+    const double r = __fma_rn(tz, A, t);
+    return __fma_rn(S, r, C);
+}
+
+template <typename T>
+__device__ __forceinline__ T atan2_t(float yf, float xf) {
+    if constexpr (sizeof(T) == 8) return atan2_f64(yf, xf);
+    else return atan2_generic<T>(yf, xf);
+}
+
 // sin and cos of an f32 argument |x| < ~100 (here |x| < 2 pi): Cody-Waite reduction by pi/2, Taylor polynomials on
 // [-pi/4, pi/4] (degree 13 / 14 in double, 9 / 10 in float)
 template <typename T>
@@ -106,6 +158,22 @@ __device__ __forceinline__ void sincos_t(float xf, T &sn, T &cs) {
     const float kf = rintf(xf * 0.63661977236758134f);
     const int q = (int)kf;
     const T k = (T)kf;
+    if constexpr (sizeof(T) == 8) {
+        // depth-first f64 variant: one-constant reduction (|k| <= 64: the dropped 6e-17 * k is far below the 1e-10 the
+        // f32 result needs), 4-term near-minimax polynomials in 2 Estrin levels (sin: relative error 1.9e-11,
+        // cos: absolute 1.9e-10 on |r| <= pi/4)
+        const double r = __fma_rn(-k, 1.5707963267948966, (double)xf);
+        const double s = r * r, s2 = s * s, rs = r * s;
+        const double S = __fma_rn(__fma_rn(2.7249925803001736e-06, s, -0.00019840086735384028), s2,
+                                  __fma_rn(0.0083333318747102047, s, -0.1666666666385529));
+        const double Cc = __fma_rn(__fma_rn(2.4463788293291526e-05, s, -0.001388758915560089), s2,
+                                   __fma_rn(0.041666650644517043, s, -0.49999999969119313));
+        const double sr = __fma_rn(rs, S, r), cr = __fma_rn(s, Cc, 1.0);
+        const double a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
+        sn = (q & 2) ? -a : a;
+        cs = ((q + 1) & 2) ? -b : b;
+        return;
+    }
     T r;
     if (sizeof(T) == 8) {
         r = fma_t(-k, T(1.5707963267948966), (T)xf);
