@@ -128,3 +128,28 @@ def test_fm_stereo_separates_left_and_right(sdr):
     # measured 8.7x and 3.6x: the reference's decode (v / nco^2 with the loop's static phase error, no pre-emphasis
     # in the generator) separates the channels without being a hi-fi decoder
     assert l1 > 3 * l3 and r3 > 3 * r1
+
+
+def test_fm_stereo_contract_and_edges(sdr):
+    with pytest.raises(sdr.SdrError):
+        sdr.FmStereo(1, 100000.0)       # below the 144 kHz intermediate rate: the chain would up-sample
+    with pytest.raises(sdr.SdrError):
+        sdr.FmStereo(0, RATE)
+    fm = sdr.FmStereo(1, RATE)
+    assert fm.process(np.empty(0, np.uint8), end_of_input=True).shape == (0, 2)   # nothing in, nothing out
+    fm.reset()                                            # end_of_input is sticky until reset (as in libsamplerate)
+    iq = gen.fm_stereo_u8(60000, RATE, 800.0, 1700.0, 3)
+    a = fm.process(iq)                                    # no flush: the converters still hold their right wings
+    b = fm.process(np.empty(0, np.uint8), end_of_input=True)   # flush only
+    one = sdr.FmStereo(1, RATE).process(iq, end_of_input=True)
+    cat = np.concatenate([a, b])
+    assert len(a) < len(one) and cat.shape == one.shape
+    assert np.abs(cat - one).max() <= 2e-6 * max(1.0, float(np.abs(one).max()))
+    # a batch of identical stations gives identical rows, equal to the single-station result bit for bit
+    two = sdr.FmStereo(2, RATE).process(np.stack([iq, iq]), end_of_input=True)
+    assert np.array_equal(two[0].view(np.uint32), two[1].view(np.uint32))
+    assert np.array_equal(two[0].view(np.uint32), one.view(np.uint32))
+    # zero-length stereo decode is a no-op
+    des = sdr.PllDesign(19000.0, 0.0002, sdr.BiquadD.LowPass(200.0, 0.7), sdr.BiquadD.LowPass(20.0, 0.7),
+                        sdr.BiquadD.LowPass(20.0, 0.7))
+    assert sdr.PllBatch([des], 1, 144000.0).stereo_decode(np.empty(0, np.float32)).shape == (0, 2)
