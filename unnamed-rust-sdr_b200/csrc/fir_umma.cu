@@ -147,6 +147,13 @@ __host__ __device__ constexpr size_t um_smem_bytes(int R, int PC, int KS, bool d
 
 // R = samples between window rows (8 / 16 / 32: no / 32-byte / 64-byte swizzle), PC = output candidates per row
 // (PC == R when D == 1), DEC = decimating epilogue.
+// work item w = ch * ntiles + tile.  The single-channel case (the u8 stream configs) skips the 64-bit division, which
+// is ~100 instructions on the per-tile path of every role.
+__device__ __forceinline__ void split_work(long long w, int ntiles, int n_ch, int &ch, long long &tile) {
+    if (n_ch == 1) { ch = 0; tile = w; }
+    else { ch = (int)(w / ntiles); tile = w - (long long)ch * ntiles; }
+}
+
 template <int R, int PC, bool DEC>
 __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a) {
     constexpr int P = R;                     // (name kept from the D == 1 derivation: outputs per row when PC == R)
@@ -202,8 +209,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
         int stage = 0;
         uint32_t ph = 0;
         for (long long w = blockIdx.x; w < nwork; w += wstride) {
-            const int ch = (int)(w / a.ntiles);
-            const long long w0 = f.first - (f.K - 1) - a.delta + (w % a.ntiles) * (long long)(TILE_ROWS * R);  // multiple of 8
+            int ch; long long wt;
+            split_work(w, a.ntiles, (int)f.n_ch, ch, wt);
+            const long long w0 = f.first - (f.K - 1) - a.delta + wt * (long long)(TILE_ROWS * R);  // multiple of 8
             const unsigned char *in = (const unsigned char *)f.in + (long long)ch * f.in_stride * 2;
             const unsigned char *hist = (const unsigned char *)f.hist + (long long)ch * f.hist_stride * 2;
             mbar_wait(empty_bar(stage), ph ^ 1u);
@@ -292,8 +300,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
         long long it = 0;
         for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
             if ((it & 1) != g) continue;
-            const int ch = (int)(w / a.ntiles);
-            const long long row0 = (w % a.ntiles) * (long long)TILE_ROWS;  // first window row of the tile
+            int ch; long long wt;
+            split_work(w, a.ntiles, (int)f.n_ch, ch, wt);
+            const long long row0 = wt * (long long)TILE_ROWS;  // first window row of the tile
             float2 *out = (float2 *)f.out + (long long)ch * f.out_stride;
             mbar_wait(accf_bar(g), aph);
             aph ^= 1u;
@@ -464,8 +473,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_planar_kernel(const Um
         uint8_t *raw0 = gen + (size_t)NST * SB + (size_t)KS * N * 32 + (size_t)16 * (DEC ? 6144 : 32 * 8 * 16);
         auto issue = [&](long long w, int slot) {
             if (w < nwork) {
-                const int ch = (int)(w / a.ntiles);
-                const long long w0 = f.first - (f.K - 1) - a.delta + (w % a.ntiles) * (long long)(TILE_ROWS * R);  // multiple of 8
+                int ch; long long wt;
+                split_work(w, a.ntiles, (int)f.n_ch, ch, wt);
+                const long long w0 = f.first - (f.K - 1) - a.delta + wt * (long long)(TILE_ROWS * R);  // multiple of 8
                 const unsigned char *in = (const unsigned char *)f.in + (long long)ch * f.in_stride * 2;
                 const unsigned char *hist = (const unsigned char *)f.hist + (long long)ch * f.hist_stride * 2;
                 uint8_t *rs = raw0 + (size_t)slot * RAWB;
@@ -579,8 +589,9 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_planar_kernel(const Um
         long long it = 0;
         for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
             if ((it & 1) != g) continue;
-            const int ch = (int)(w / a.ntiles);
-            const long long row0 = (w % a.ntiles) * (long long)TILE_ROWS;
+            int ch; long long wt;
+            split_work(w, a.ntiles, (int)f.n_ch, ch, wt);
+            const long long row0 = wt * (long long)TILE_ROWS;
             float2 *out = (float2 *)f.out + (long long)ch * f.out_stride;
             mbar_wait(accf_bar(g), aph);
             aph ^= 1u;
@@ -777,20 +788,30 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
         const int RAWB = SB;
         auto issue = [&](long long w, int slot) {
             if (w < nwork) {
-                const int ch = (int)(w / a.ntiles);
+                int ch; long long wt;
+                split_work(w, a.ntiles, (int)f.n_ch, ch, wt);
                 // first raw sample of the tile; A0 = first - (K-1) - delta is a multiple of 8
-                const long long w0 = f.first - (f.K - 1) - a.delta + (w % a.ntiles) * (long long)(UP_TILE_OUT * D);
+                const long long w0 = f.first - (f.K - 1) - a.delta + wt * (long long)(UP_TILE_OUT * D);
                 const unsigned char *in = (const unsigned char *)f.in + (long long)ch * f.in_stride * 2;
                 const unsigned char *hist = (const unsigned char *)f.hist + (long long)ch * f.hist_stride * 2;
                 uint8_t *rs = raw0 + (size_t)slot * RAWB;
                 const uint32_t rs_s = smem_u32(rs);
                 const bool interior = w0 >= 0 && w0 + 8LL * nunits * D <= f.n_in;
-                for (int v = ptid; v < nunits; v += 32 * UP_PROD_WARPS) {
+                if (interior) {
+                    // the common case, kept free of the boundary code: a lane's D chunks are 16 D contiguous bytes
+                    for (int v = ptid; v < nunits; v += 32 * UP_PROD_WARPS) {
+                        const unsigned char *src = in + 2 * (w0 + 8LL * v * D);
+                        const uint32_t dst = rs_s + 16u * (uint32_t)(v * D);
 #pragma unroll
+                        for (int c = 0; c < D; ++c) cp_async16_s(dst + 16u * c, src + 16 * c);
+                    }
+                } else
+                for (int v = ptid; v < nunits; v += 32 * UP_PROD_WARPS) {
+#pragma unroll 1
                     for (int c = 0; c < D; ++c) {
                         const int q = v * D + c;
                         const long long s0 = w0 + 8LL * q;
-                        if (interior || (s0 >= 0 && s0 + 8 <= f.n_in)) {
+                        if (s0 >= 0 && s0 + 8 <= f.n_in) {
                             cp_async16_s(rs_s + 16u * q, in + 2 * s0);
                         } else if (s0 < f.n_in) {
                             unsigned short h[8];
@@ -898,8 +919,9 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
         for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
             if ((it & 1) != wg) continue;
             const int set = (int)(it & (UP_SETS - 1));
-            const int ch = (int)(w / a.ntiles);
-            const long long m0 = (w % a.ntiles) * (long long)UP_TILE_OUT;
+            int ch; long long wt;
+            split_work(w, a.ntiles, (int)f.n_ch, ch, wt);
+            const long long m0 = wt * (long long)UP_TILE_OUT;
             float2 *out = (float2 *)f.out + (long long)ch * f.out_stride;
             mbar_wait(accf_bar(set), aph);
             if (set >= 2) aph ^= 1u;  // this warpgroup's two sets alternate; the parity flips after both were used
