@@ -729,9 +729,18 @@ constexpr int UP_SETS = 4;         // accumulator sets of 48 TMEM columns
 constexpr int UP_RAW = 3;          // raw ring slots: cp.async runs 2 tiles ahead (deeper rings measured no better)
 __host__ __device__ constexpr int up_ksteps(int K, int D) { return (7 + (K + 6) / D) / 16 + 1; }
 __host__ __device__ constexpr int up_nsub(int KS) { return 8 * 128 + 16 * KS; }  // sub-samples per plane per tile
+// A producer lane reads the D raw chunks of ITS unit v (chunks v*D .. v*D + D-1) with LDS.128; for even D the lane stride
+// of 16 D bytes puts the 8 lanes of a quarter warp on 8 / gcd(D, 8) bank groups (2-way conflicts at D = 10, 8-way at
+// D = 8; ncu: 35 % of the kernel's shared wavefronts were replays).  The raw ring is therefore skewed: unit v lives
+// up_skew(D, v) chunks further on.  The same lane writes (cp.async) and reads a unit, so only its own address changes.
+__host__ __device__ constexpr int up_gcd8(int D) { return (D % 8 == 0) ? 8 : (D % 4 == 0) ? 4 : (D % 2 == 0) ? 2 : 1; }
+__host__ __device__ constexpr int up_skew(int D, int v) { return (v * up_gcd8(D)) >> 3; }
+__host__ __device__ constexpr size_t up_raw_bytes(int D, int KS) {
+    return (size_t)D * 2 * up_nsub(KS) + 16 * (size_t)(up_skew(D, up_nsub(KS) / 8) + 1);
+}
 __host__ __device__ constexpr size_t up_smem_bytes(int D, int KS, int stages) {
-    // stages of D planes + tables + raw ring (UP_RAW slots, same size as a stage) + 1 KB slack + barriers
-    return (size_t)(stages + UP_RAW) * D * 2 * up_nsub(KS) + (size_t)D * KS * 48 * 32 + 1024 + 256;
+    // stages of D planes + tables + raw ring (UP_RAW skewed slots) + 1 KB slack + barriers
+    return (size_t)stages * D * 2 * up_nsub(KS) + UP_RAW * up_raw_bytes(D, KS) + (size_t)D * KS * 48 * 32 + 1024 + 256;
 }
 
 // roles: 8 producer warps (the phase split is the heavy part here), 2 MMA warps taking alternate tiles (a small-N
@@ -785,7 +794,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
         // ================= producers: raw ring (cp.async, two tiles ahead) -> D phase planes =================
         const int ptid = warp * 32 + lane;
         const int nunits = NSUB / 8;  // a unit = 8 sub-samples of every phase = D raw chunks = D plane chunks
-        const int RAWB = SB;
+        const int RAWB = (int)up_raw_bytes(D, KS);
         auto issue = [&](long long w, int slot) {
             if (w < nwork) {
                 int ch; long long wt;
@@ -801,7 +810,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
                     // the common case, kept free of the boundary code: a lane's D chunks are 16 D contiguous bytes
                     for (int v = ptid; v < nunits; v += 32 * UP_PROD_WARPS) {
                         const unsigned char *src = in + 2 * (w0 + 8LL * v * D);
-                        const uint32_t dst = rs_s + 16u * (uint32_t)(v * D);
+                        const uint32_t dst = rs_s + 16u * (uint32_t)(v * D + up_skew(D, v));
 #pragma unroll
                         for (int c = 0; c < D; ++c) cp_async16_s(dst + 16u * c, src + 16 * c);
                     }
@@ -811,8 +820,9 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
                     for (int c = 0; c < D; ++c) {
                         const int q = v * D + c;
                         const long long s0 = w0 + 8LL * q;
+                        const int qs = q + up_skew(D, v);  // skewed slot of the chunk
                         if (s0 >= 0 && s0 + 8 <= f.n_in) {
-                            cp_async16_s(rs_s + 16u * q, in + 2 * s0);
+                            cp_async16_s(rs_s + 16u * qs, in + 2 * s0);
                         } else if (s0 < f.n_in) {
                             unsigned short h[8];
 #pragma unroll
@@ -826,7 +836,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
                             uint4 qv;
                             qv.x = h[0] | ((unsigned)h[1] << 16); qv.y = h[2] | ((unsigned)h[3] << 16);
                             qv.z = h[4] | ((unsigned)h[5] << 16); qv.w = h[6] | ((unsigned)h[7] << 16);
-                            *reinterpret_cast<uint4 *>(rs + 16 * q) = qv;  // read back by this same lane
+                            *reinterpret_cast<uint4 *>(rs + 16 * qs) = qv;  // read back by this same lane
                         }
                     }
                 }
@@ -849,7 +859,7 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
                 uint32_t rw[4 * D];  // the unit's 8 D samples, 2 per word (I, Q bytes of a sample stay together)
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(rs + 16 * (v * D + c));
+                    const uint4 q = *reinterpret_cast<const uint4 *>(rs + 16 * (v * D + up_skew(D, v) + c));
                     rw[4 * c] = q.x; rw[4 * c + 1] = q.y; rw[4 * c + 2] = q.z; rw[4 * c + 3] = q.w;
                 }
 #pragma unroll
