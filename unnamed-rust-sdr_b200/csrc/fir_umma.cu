@@ -336,6 +336,34 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(acce_bar(g));
                 }
+                if constexpr (!DEC) {
+                    // D == 1: output index = (row0 + row) * P + u.  Everything but (16 hh + 8 rs) * P + 4 cg is folded
+                    // into one per-thread pointer per piece, so a store is STG [base + immediate]; a tile that lies
+                    // entirely inside the call (all but the last) needs no per-output bound test either.  (Computing
+                    // index, address and bound per output cost as many instructions as the conversion itself in this
+                    // epilogue-bound kernel.)
+                    const long long m_base = row0 * (long long)P + (long long)(mb * 128 + quad * 32 + (lane >> 2)) * P +
+                                             8 * pc + (lane & 3);
+                    float2 *ob = out + m_base;
+                    const long long left = f.n_out - m_base;  // outputs from this thread's first one to the end
+                    const bool full = left > (long long)(24 * P + 4);
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh)
+#pragma unroll
+                        for (int cg = 0; cg < 2; ++cg)
+#pragma unroll
+                            for (int rs = 0; rs < 2; ++rs) {
+                                const int i0 = 4 * cg + 2 * rs;
+                                const int off = (16 * hh + 8 * rs) * P + 4 * cg;
+                                if (full || (long long)off < left) {
+                                    const float fI = (float)((int)(e[hh][1][i0] << 8) + (int)e[hh][0][i0] + c10[0]);
+                                    const float fQ = (float)((int)(e[hh][1][i0 + 1] << 8) + (int)e[hh][0][i0 + 1] + c10[1]);
+                                    const float gI = __int_as_float((int)e[hh][2][i0] + m2[0]) - 12582912.0f;
+                                    const float gQ = __int_as_float((int)e[hh][2][i0 + 1] + m2[1]) - 12582912.0f;
+                                    ob[off] = make_float2(fmaf(gI, sc2, fI * sc0), fmaf(gQ, sc2, fQ * sc0));
+                                }
+                            }
+                } else
 #pragma unroll
                 for (int hh = 0; hh < 2; ++hh)
 #pragma unroll
