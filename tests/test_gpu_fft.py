@@ -65,9 +65,14 @@ def test_fused_u8_unpack(sdr, n):
     x = O.unpack_u8iq(raw).reshape(batches, n)
     got = sdr.FftPlan(n, "u8iq", shift=True, norm=True).exec(raw)
     check(got, x, shift=True, norm=True)
-    # fused unpack == unpack then c64 transform, bit for bit
+    # fused unpack == unpack then c64 transform: bit for bit where both formats run the same arithmetic; at 1024 the u8
+    # kernel uses packed complex adds (FADD2, no mul+add contraction across them) and the c64 kernel does not (each
+    # measured faster that way), so the last bit may differ there
     two = sdr.FftPlan(n, "c64", shift=True, norm=True).exec(x)
-    assert np.array_equal(got.view(np.uint32), two.view(np.uint32))
+    if n == 1024:
+        assert np.abs(got - two).max() <= 4e-7 * np.abs(two).max()
+    else:
+        assert np.array_equal(got.view(np.uint32), two.view(np.uint32))
 
 
 def test_tone_known_answer_and_labels(sdr):

@@ -99,6 +99,21 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// sm_100 packed FP32: one FADD2 per complex add / subtract.  Same flops per cycle as two FADDs (FADD2 issues at half
+// rate, profiles/r01_f32x2_rate_probe.txt) but half the issue slots -- a gain for the issue-bound FFT kernels, a loss
+// for some others (measured per kernel, see fft.cu), hence a template switch rather than a global one.
+__device__ __forceinline__ float2 cadd_p(float2 a, float2 b) {
+    unsigned long long r;
+    asm("add.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+__device__ __forceinline__ float2 csub_p(float2 a, float2 b) {
+    unsigned long long r;
+    asm("sub.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<unsigned long long *>(&a)), "l"(*reinterpret_cast<unsigned long long *>(&b)));
+    return *reinterpret_cast<float2 *>(&r);
+}
+template <bool PK> __device__ __forceinline__ float2 cadd_t(float2 a, float2 b) { return PK ? cadd_p(a, b) : cadd(a, b); }
+template <bool PK> __device__ __forceinline__ float2 csub_t(float2 a, float2 b) { return PK ? csub_p(a, b) : csub(a, b); }
 
 #endif  // __CUDACC__
 

@@ -28,43 +28,44 @@ constexpr float C_SIN_PI_8 = 0.38268343236508977173f;
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }  // a * (-i)
 
 // forward 4-point DFT in place on a, b, c, d -> X0..X3
+template <bool PK = false>
 __device__ __forceinline__ void dft4(float2 &a, float2 &b, float2 &c, float2 &d) {
-    const float2 s02 = cadd(a, c), d02 = csub(a, c), s13 = cadd(b, d), d13 = mul_mi(csub(b, d));
-    a = cadd(s02, s13);
-    b = cadd(d02, d13);
-    c = csub(s02, s13);
-    d = csub(d02, d13);
+    const float2 s02 = cadd_t<PK>(a, c), d02 = csub_t<PK>(a, c), s13 = cadd_t<PK>(b, d), d13 = mul_mi(csub_t<PK>(b, d));
+    a = cadd_t<PK>(s02, s13);
+    b = cadd_t<PK>(d02, d13);
+    c = csub_t<PK>(s02, s13);
+    d = csub_t<PK>(d02, d13);
 }
 
 // R-point forward DFT over v[0], v[S], ..., v[(R-1)S]; natural order in and out.
-template <int R, int S>
+template <int R, int S, bool PK = false>
 __device__ __forceinline__ void dft(float2 *v) {
     if (R == 2) {
         const float2 a = v[0], b = v[S];
-        v[0] = cadd(a, b);
-        v[S] = csub(a, b);
+        v[0] = cadd_t<PK>(a, b);
+        v[S] = csub_t<PK>(a, b);
     } else if (R == 4) {
-        dft4(v[0], v[S], v[2 * S], v[3 * S]);
+        dft4<PK>(v[0], v[S], v[2 * S], v[3 * S]);
     } else if (R == 8) {
         // n = c + 2a: U[c][r] = DFT4_a(v[c+2a]); X[r] = U0[r] + W8^r U1[r]; X[r+4] = U0[r] - W8^r U1[r]
         float2 e0 = v[0], e1 = v[2 * S], e2 = v[4 * S], e3 = v[6 * S];
         float2 o0 = v[S], o1 = v[3 * S], o2 = v[5 * S], o3 = v[7 * S];
-        dft4(e0, e1, e2, e3);
-        dft4(o0, o1, o2, o3);
+        dft4<PK>(e0, e1, e2, e3);
+        dft4<PK>(o0, o1, o2, o3);
         o1 = make_float2((o1.x + o1.y) * C_SQRT1_2, (o1.y - o1.x) * C_SQRT1_2);   // * W8^1 = (1-i)/sqrt2
         o2 = mul_mi(o2);                                                          // * W8^2 = -i
         o3 = make_float2((o3.y - o3.x) * C_SQRT1_2, -(o3.x + o3.y) * C_SQRT1_2);  // * W8^3 = (-1-i)/sqrt2
-        v[0] = cadd(e0, o0); v[4 * S] = csub(e0, o0);
-        v[S] = cadd(e1, o1); v[5 * S] = csub(e1, o1);
-        v[2 * S] = cadd(e2, o2); v[6 * S] = csub(e2, o2);
-        v[3 * S] = cadd(e3, o3); v[7 * S] = csub(e3, o3);
+        v[0] = cadd_t<PK>(e0, o0); v[4 * S] = csub_t<PK>(e0, o0);
+        v[S] = cadd_t<PK>(e1, o1); v[5 * S] = csub_t<PK>(e1, o1);
+        v[2 * S] = cadd_t<PK>(e2, o2); v[6 * S] = csub_t<PK>(e2, o2);
+        v[3 * S] = cadd_t<PK>(e3, o3); v[7 * S] = csub_t<PK>(e3, o3);
     } else {  // R == 16, S == 1
         // n = c + 4a: U[c][r] = DFT4_a(v[c+4a]); X[r+4q] = DFT4_c(W16^{c r} U[c][r])[q]
         float2 u[4][4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             u[c][0] = v[c * S]; u[c][1] = v[(c + 4) * S]; u[c][2] = v[(c + 8) * S]; u[c][3] = v[(c + 12) * S];
-            dft4(u[c][0], u[c][1], u[c][2], u[c][3]);
+            dft4<PK>(u[c][0], u[c][1], u[c][2], u[c][3]);
         }
         const float2 w1 = make_float2(C_COS_PI_8, -C_SIN_PI_8);
         const float2 w2 = make_float2(C_SQRT1_2, -C_SQRT1_2);
@@ -76,7 +77,7 @@ __device__ __forceinline__ void dft(float2 *v) {
         u[3][1] = cmul(u[3][1], w3); u[3][2] = cmul(u[3][2], w6); u[3][3] = cmul(u[3][3], w9);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            dft4(u[0][r], u[1][r], u[2][r], u[3][r]);
+            dft4<PK>(u[0][r], u[1][r], u[2][r], u[3][r]);
             v[r * S] = u[0][r]; v[(r + 4) * S] = u[1][r]; v[(r + 8) * S] = u[2][r]; v[(r + 12) * S] = u[3][r];
         }
     }
@@ -200,9 +201,10 @@ __host__ __device__ constexpr float w32_sin(int r) { return r <= 8 ? w32_q(8 - r
 
 // 32-point forward DFT, v (natural order) -> w (natural order).  n = c + 2a: two 16-point DFTs over the even
 // and odd inputs, then X[r] = U0[r] + W32^r U1[r], X[r+16] = U0[r] - W32^r U1[r].
+template <bool PK = false>
 __device__ __forceinline__ void dft32(float2 (&v)[32], float2 (&w)[32]) {
-    dft<16, 2>(v);
-    dft<16, 2>(v + 1);
+    dft<16, 2, PK>(v);
+    dft<16, 2, PK>(v + 1);
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
         const float2 u0 = v[2 * r], u1 = v[2 * r + 1];
@@ -212,8 +214,8 @@ __device__ __forceinline__ void dft32(float2 (&v)[32], float2 (&w)[32]) {
         else if (r == 4) t = make_float2((u1.x + u1.y) * C_SQRT1_2, (u1.y - u1.x) * C_SQRT1_2);
         else if (r == 12) t = make_float2((u1.y - u1.x) * C_SQRT1_2, -(u1.x + u1.y) * C_SQRT1_2);
         else t = cmul(u1, make_float2(w32_cos(r), -w32_sin(r)));
-        w[r] = cadd(u0, t);
-        w[r + 16] = csub(u0, t);
+        w[r] = cadd_t<PK>(u0, t);
+        w[r + 16] = csub_t<PK>(u0, t);
     }
 }
 
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(W1K_WARPS * 32, 2) fft1024_warp_kernel(FftArgs
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = __ldg(src + 32 * e);
         }
-        dft32(v, w);
+        dft32<FMT == SDR_FMT_U8IQ>(v, w);  // packed complex adds: +4 % for u8 input, -8 % for c64 (measured)
 #pragma unroll
         for (int s = 0; s < 32; ++s) xch[33 * lane + s] = w[s];
         __syncwarp();
@@ -296,7 +298,7 @@ __global__ void __launch_bounds__(W1K_WARPS * 32, 2) fft1024_warp_kernel(FftArgs
 #pragma unroll
         for (int q = 1; q < 32; ++q) v[q] = cmul(v[q], tw_s[(q - 1) * 32 + lane]);
         if (FMT != SDR_FMT_U8IQ && norm) { v[0].x *= fold; v[0].y *= fold; }
-        dft32(v, w);
+        dft32<FMT == SDR_FMT_U8IQ>(v, w);
         float2 *dst = a.out + b * N + lane;
 #pragma unroll
         for (int s = 0; s < 32; ++s) dst[32 * (shift ? (s ^ 16) : s)] = w[s];
@@ -344,6 +346,8 @@ struct Reg2Plan {
     static constexpr int THREADS = TC > 256 ? TC : 256;
     static constexpr int SEQ = THREADS / TC;
     static constexpr int NP = (LOGN + 3) / 4;                 // passes
+    // FADD2 / packed complex adds (common.cuh): measured per size on one box, +3 % at 256 and 4096, -4 % at 8192
+    static constexpr bool PACKED = LOGN != 13;
     static constexpr int RLAST = 1 << (LOGN - 4 * (NP - 1));  // radix of the last pass (16 if LOGN % 4 == 0)
     static constexpr int NBLAST = 16 / RLAST;
     // shared twiddle tables of the middle passes (pass j, 1 <= j <= NP-2): 15 * 16^j entries each
@@ -369,6 +373,7 @@ __device__ __forceinline__ float2 raw_elem(const unsigned char *raw, int idx) {
 // middle pass j (sub-size p = 16^j, radix 16): shared -> registers -> shared
 template <int LOGN, int PLOG>
 __device__ __forceinline__ void reg2_middle(float2 *sx, const float2 *tab, int t, int group) {
+    constexpr bool PK = Reg2Plan<LOGN>::PACKED;
     constexpr int N = 1 << LOGN, TC = N / 16, p = 1 << PLOG;
     float2 v[16];
 #pragma unroll
@@ -376,7 +381,7 @@ __device__ __forceinline__ void reg2_middle(float2 *sx, const float2 *tab, int t
     const int k = t & (p - 1);
 #pragma unroll
     for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tab[(q - 1) * p + k]);
-    dft<16, 1>(v);
+    dft<16, 1, PK>(v);
     group_sync<TC>(group);
     const int base = (t - k) * 16 + k;
 #pragma unroll
@@ -449,7 +454,7 @@ fft_reg2_kernel(FftArgs a) {
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = live ? load_elem<FMT>(a.in, b * N + t + e * TC) : make_float2(0.f, 0.f);
         }
-        dft<16, 1>(v);
+        dft<16, 1, PL::PACKED>(v);
         if (NP == 1) {
             // (N == 16 is not dispatched here)
         }
@@ -467,7 +472,7 @@ fft_reg2_kernel(FftArgs a) {
 #pragma unroll
             for (int q = 1; q < RL; ++q) v[vi + q * NBL] = cmul(v[vi + q * NBL], twl[vi][q - 1]);
 #pragma unroll
-        for (int vi = 0; vi < NBL; ++vi) dft<RL, NBL>(v + vi);
+        for (int vi = 0; vi < NBL; ++vi) dft<RL, NBL, PL::PACKED>(v + vi);
         if (live) {
             float2 *dst = a.out + b * out_len;
 #pragma unroll
@@ -631,7 +636,7 @@ __global__ void __launch_bounds__(256, 4) fft_l2_kernel(FftArgs a, int lag, long
                 const long long src = b * n + col0 + c + (long long)rr * N2;
 #pragma unroll
                 for (int e = 0; e < 16; ++e) v[e] = load_elem<FMT>(a.in, src + (long long)e * 16 * N2);
-                dft<16, 1>(v);
+                dft<16, 1, true>(v);
                 float2 *dst = sm + c * PL::SSTRIDE0;
 #pragma unroll
                 for (int q = 0; q < 16; ++q) dst[pad(16 * rr + q)] = v[q];
@@ -644,7 +649,7 @@ __global__ void __launch_bounds__(256, 4) fft_l2_kernel(FftArgs a, int lag, long
                 for (int e = 0; e < 16; ++e) v[e] = srcs[pad(t + 16 * e)];
 #pragma unroll
                 for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw0[(q - 1) * 16 + t]);
-                dft<16, 1>(v);
+                dft<16, 1, true>(v);
                 float2 *dst = a.out + b * n + 256LL * (col0 + col) + t;
 #pragma unroll
                 for (int q = 0; q < 16; ++q) dst[16 * q] = v[q];
@@ -680,7 +685,7 @@ __global__ void __launch_bounds__(256, 4) fft_l2_kernel(FftArgs a, int lag, long
 #pragma unroll
                 for (int e = 0; e < 16; ++e) v[e] = cmul(v[e], tw[e]);
             }
-            dft<16, 1>(v);
+            dft<16, 1, true>(v);
             float2 *col = sm + c * PL::SSTRIDE1;
 #pragma unroll
             for (int q = 0; q < 16; ++q) col[pad(16 * t + q)] = v[q];
@@ -694,7 +699,7 @@ __global__ void __launch_bounds__(256, 4) fft_l2_kernel(FftArgs a, int lag, long
                 for (int q = 1; q < R2; ++q) v[vi + q * NB2] = cmul(v[vi + q * NB2], tw1[(q - 1) * 16 + kk]);
             }
 #pragma unroll
-            for (int vi = 0; vi < NB2; ++vi) dft<R2, NB2>(v + vi);
+            for (int vi = 0; vi < NB2; ++vi) dft<R2, NB2, true>(v + vi);
             float2 *ob = a.out + b * n + k;
 #pragma unroll
             for (int vi = 0; vi < NB2; ++vi)
