@@ -29,7 +29,7 @@ import numpy as np  # noqa: E402
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the `ncu --set full` captures
 # summarised under profiles/ (same command line as the bench, one launch).  null = not captured for that workload.
 NCU_TRAFFIC = {
-    "c2_fft1024_u8iq_2p28": (2.628e9, "profiles/r01_prof_fft1024_u8_v3.txt"),
+    "c2_fft1024_u8iq_2p28": (2.6255e9, "profiles/r01f_ncu_fft1024_u8.txt"),
     "fir64_d1_u8iq_2p26": (6.124e8, "profiles/r01_prof_fir_umma_c1_v2.txt"),
     "fir255_d1_u8iq_2p26": (6.122e8, "profiles/r01_prof_fir_umma_k255_v2.txt"),
     "c5_fft65536_c64_2p27": (2.102e9, "profiles/r01_prof_fft_l2_64k_v1.txt"),
