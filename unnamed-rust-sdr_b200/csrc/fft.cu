@@ -375,17 +375,22 @@ template <int LOGN, int PLOG>
 __device__ __forceinline__ void reg2_middle(float2 *sx, const float2 *tab, int t, int group) {
     constexpr bool PK = Reg2Plan<LOGN>::PACKED;
     constexpr int N = 1 << LOGN, TC = N / 16, p = 1 << PLOG;
+    // pad(a + c) = pad(a) + c + c/16 when c is a multiple of 16 (no carry out of the low nibble): one pad() per pass,
+    // the 16 elements at immediate offsets (the per-element shifts were a fifth of this kernel's issue slots)
+    static_assert(TC % 16 == 0 && p % 16 == 0, "padded offsets");
     float2 v[16];
+    const float2 *ld = sx + pad(t);
 #pragma unroll
-    for (int e = 0; e < 16; ++e) v[e] = sx[pad(t + e * TC)];
+    for (int e = 0; e < 16; ++e) v[e] = ld[e * (TC + TC / 16)];
     const int k = t & (p - 1);
 #pragma unroll
     for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tab[(q - 1) * p + k]);
     dft<16, 1, PK>(v);
     group_sync<TC>(group);
     const int base = (t - k) * 16 + k;
+    float2 *stp = sx + pad(base);
 #pragma unroll
-    for (int q = 0; q < 16; ++q) sx[pad(base + q * p)] = v[q];
+    for (int q = 0; q < 16; ++q) stp[q * (p + p / 16)] = v[q];
     group_sync<TC>(group);
 }
 
@@ -458,15 +463,21 @@ fft_reg2_kernel(FftArgs a) {
         if (NP == 1) {
             // (N == 16 is not dispatched here)
         }
+        {
+            float2 *st0 = sx + 17 * t;  // pad(16 t + q) = 17 t + q for q < 16
 #pragma unroll
-        for (int q = 0; q < 16; ++q) sx[pad(16 * t + q)] = v[q];
+            for (int q = 0; q < 16; ++q) st0[q] = v[q];
+        }
         group_sync<TC>(group);
         // ---- middle passes ----
         if (NP >= 3) reg2_middle<LOGN, 4>(sx, tabs, t, group);
         if (NP >= 4) reg2_middle<LOGN, 8>(sx, tabs + 15 * 16, t, group);
         // ---- last pass: shared -> registers, per-thread twiddles, registers -> global ----
+        {
+            const float2 *ld = sx + pad(t);  // pad(t + e TC) = pad(t) + e (TC + TC/16), TC a multiple of 16
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = sx[pad(t + e * TC)];
+            for (int e = 0; e < 16; ++e) v[e] = ld[e * (TC + TC / 16)];
+        }
 #pragma unroll
         for (int vi = 0; vi < NBL; ++vi)
 #pragma unroll
