@@ -650,14 +650,14 @@ __global__ void __launch_bounds__(256, 4) fft_l2_kernel(FftArgs a, int lag, long
                 dft<16, 1, true>(v);
                 float2 *dst = sm + c * PL::SSTRIDE0;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) dst[pad(16 * rr + q)] = v[q];
+                for (int q = 0; q < 16; ++q) dst[17 * rr + q] = v[q];  // pad(16 rr + q) = 17 rr + q
             }
             __syncthreads();
             {
                 const int col = tid >> 4, t = tid & 15;
                 const float2 *srcs = sm + col * PL::SSTRIDE0;
 #pragma unroll
-                for (int e = 0; e < 16; ++e) v[e] = srcs[pad(t + 16 * e)];
+                for (int e = 0; e < 16; ++e) v[e] = srcs[t + 17 * e];  // pad(t + 16 e) = t + 17 e for t < 16
 #pragma unroll
                 for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw0[(q - 1) * 16 + t]);
                 dft<16, 1, true>(v);
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(256, 4) fft_l2_kernel(FftArgs a, int lag, long
             dft<16, 1, true>(v);
             float2 *col = sm + c * PL::SSTRIDE1;
 #pragma unroll
-            for (int q = 0; q < 16; ++q) col[pad(16 * t + q)] = v[q];
+            for (int q = 0; q < 16; ++q) col[17 * t + q] = v[q];  // pad(16 t + q) = 17 t + q
             __syncthreads();
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = col[pad(t + e * TC)];
