@@ -244,6 +244,28 @@ int main() {
         EXPECT(bad == 0, "FmStereo vs stage-by-stage chain: %zu frames differ", bad);
     }
 
+    // ---- live.rs:30-39: window(d).decimate(fps).map(fft) in one call == fft::fft of each kept window, bit for bit ----
+    {
+        const float rate = 300000.0f;
+        const size_t n = 35000;
+        std::vector<Complex> x(n);
+        for (size_t i = 0; i < n; ++i) x[i] = Complex((float)std::cos(0.8 * i) + 0.1f * (float)std::sin(0.013 * i), (float)std::sin(0.8 * i));
+        fft::WindowSpectra ws(rate, 1000.0f / rate, 30.0f);  // window 1000, hop 10000
+        std::vector<Complex> spectra;
+        size_t got = ws.process(x.data(), 12345, spectra);
+        got += ws.process(x.data() + 12345, n - 12345, spectra);
+        EXPECT(ws.window() == 1000 && got == 3 && spectra.size() == 3000, "WindowSpectra count %zu", got);
+        size_t bad = 0;
+        for (size_t j = 0; j < got; ++j) {
+            const size_t e = (j + 1) * 10000 - 1;  // last sample of kept window j
+            std::vector<Complex> w(x.begin() + (e + 1 - 1000), x.begin() + e + 1);
+            auto f = fft::fft(signal::from_iter<Complex>(rate, w));
+            for (size_t i = 0; i < 1000; ++i)
+                if (std::memcmp(&f[i].second, &spectra[j * 1000 + i], sizeof(Complex))) ++bad;
+        }
+        EXPECT(bad == 0, "WindowSpectra vs fft::fft of each window: %zu values differ", bad);
+    }
+
     printf(fails ? "HOST MIRROR: %d failure(s)\n" : "HOST MIRROR OK\n", fails);
     return fails ? 1 : 0;
 }

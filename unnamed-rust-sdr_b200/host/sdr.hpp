@@ -605,6 +605,42 @@ inline std::vector<std::pair<float, Complex>> rfft(signal::Sig<float> input) {
     return collated;
 }
 
+// signal.window(duration).decimate(fps).map(|w| fft::fft(w)) of examples/live.rs:30-39 behind sdr_window_fft_*:
+// feed blocks of samples, get the kept windows' spectra (each `window()` values, shifted and 1/sqrt(N)-scaled like
+// fft::fft) back to back.  window = (duration * rate).round() (adapters/mod.rs:279), hop = Decimate's wait (mod.rs:22).
+class WindowSpectra {
+    sdr_window_fft_t *h_ = nullptr;
+    size_t n_ = 0;
+
+  public:
+    WindowSpectra(float rate, float duration, float fps, bool u8iq = false) {
+        sdr_window_fft_config_t cfg{};
+        cfg.window = sdr_duration_samples(rate, duration);
+        cfg.hop = sdr_decimate_wait(rate, fps);
+        cfg.input_format = u8iq ? SDR_FMT_U8IQ : SDR_FMT_C64;
+        cfg.flags = SDR_FFT_SHIFT | SDR_FFT_NORM;
+        int err = 0;
+        h_ = sdr_window_fft_create(&cfg, &err);
+        if (!h_) throw Error(err, "WindowSpectra::new");
+        n_ = cfg.window;
+    }
+    WindowSpectra(const WindowSpectra &) = delete;
+    WindowSpectra &operator=(const WindowSpectra &) = delete;
+    ~WindowSpectra() { sdr_window_fft_destroy(h_); }
+    size_t window() const { return n_; }
+    // in: n samples (Complex, or 2n bytes when constructed with u8iq); returns the number of spectra appended to out
+    size_t process(const void *in, size_t n, std::vector<Complex> &out) {
+        const size_t nw = sdr_window_fft_output_count(h_, n);
+        const size_t at = out.size();
+        out.resize(at + nw * n_);
+        size_t got = 0;
+        Complex dummy;
+        check(sdr_window_fft_process(h_, in, n, reinterpret_cast<float *>(nw ? out.data() + at : &dummy), nw, &got),
+              "WindowSpectra::process");
+        return got;
+    }
+};
+
 }  // namespace fft
 
 // =========================================================================================
