@@ -19,10 +19,16 @@ y = O.Fir(taps255).apply(O.unpack_u8iq(fm))[9::10]
 fr, v = O.freq_sweep(1800000.0, 20000.0, True, -200000.0, 200000.0)
 d = O.pll_design(0.0, 0.035, (O.BQ_LOWPASS, 80000.0, 0.7), (O.BQ_LOWPASS, 20000.0, 0.7), (O.BQ_LOWPASS, 20000.0, 0.7))
 out, lk = O.Pll(d, 1.8e6).apply(v)
+# FM stereo decode (src/main.rs:62-71) around the pilot Pll, on a small synthetic multiplex at 144 kHz
+tt = np.arange(6000) / 144000.0
+mpx = (0.25 * np.sin(2 * np.pi * 1000 * tt) + 0.1 * np.sin(2 * np.pi * 19000 * tt) +
+       0.2 * np.sin(2 * np.pi * 700 * tt) * np.sin(2 * np.pi * 38000 * tt)).astype(np.float32)
+pd = O.pll_design(19000.0, 0.0002, (O.BQ_LOWPASS, 200.0, 0.7), (O.BQ_LOWPASS, 20.0, 0.7), (O.BQ_LOWPASS, 20.0, 0.7))
+stereo = O.Pll(pd, np.float32(144000.0)).stereo_decode(mpx)
 np.savez_compressed(
     os.path.join(HERE, "oracle_golden.npz"),
     c1_iq=iq, c1_fir64=O.Fir(taps64).apply(O.unpack_u8iq(iq)), c2_fft1024=O.fft_batch_u8(iq, 1024, 1),
     c3_iq=fm, c3_fir255_dec10=y, c3_resampled=O.resample_signal(y, O.SRC_SINC_FASTEST, 0.2),
     sweep_freq=fr, sweep=v, pll_out=out, pll_locked=lk,
-    bq_lp80k=O.biquad_design(O.BQ_LOWPASS, 80000.0, 0.7, 1.8e6))
+    bq_lp80k=O.biquad_design(O.BQ_LOWPASS, 80000.0, 0.7, 1.8e6), fm_mpx=mpx, fm_mono_diff=stereo)
 print("wrote", os.path.join(HERE, "oracle_golden.npz"))

@@ -279,3 +279,31 @@ def test_golden_fixtures():
     out, lk = O.Pll(d, 1.8e6).apply(v)
     assert np.array_equal(g["pll_out"], out) and np.array_equal(g["pll_locked"], lk)
     assert np.array_equal(g["bq_lp80k"], O.biquad_design(O.BQ_LOWPASS, 80000.0, 0.7, 1.8e6))
+    pd = O.pll_design(19000.0, 0.0002, (O.BQ_LOWPASS, 200.0, 0.7), (O.BQ_LOWPASS, 20.0, 0.7), (O.BQ_LOWPASS, 20.0, 0.7))
+    assert np.array_equal(g["fm_mono_diff"], O.Pll(pd, np.float32(144000.0)).stereo_decode(g["fm_mpx"]))
+
+
+def test_fm_stereo_decode_against_a_python_restatement():
+    """orc_fm_stereo_decode == the closure of src/main.rs:62-71 written out in numpy f32 around Pll::apply one sample at a
+    time: mono = v * 0.5; Some(_) => (v / value.powi(2)).re * 0.5 with num-complex's z*z and f32 / Complex formulas."""
+    n = 4000
+    tt = np.arange(n) / 144000.0
+    v = (0.3 * np.sin(2 * np.pi * 1500 * tt) + 0.1 * np.sin(2 * np.pi * 19000 * tt) +
+         0.25 * np.sin(2 * np.pi * 400 * tt) * np.sin(2 * np.pi * 38000 * tt)).astype(np.float32)
+    pd = O.pll_design(19000.0, 0.0002, (O.BQ_LOWPASS, 200.0, 0.7), (O.BQ_LOWPASS, 20.0, 0.7), (O.BQ_LOWPASS, 20.0, 0.7))
+    got = O.Pll(pd, np.float32(144000.0)).stereo_decode(v)
+    p = O.Pll(pd, np.float32(144000.0))
+    want = np.zeros((n, 2), np.float32)
+    f = np.float32
+    for i in range(n):
+        _, lk = p.apply(np.array([complex(v[i], 0.0)], np.complex64))
+        _, val = p.state()
+        want[i, 0] = v[i] * f(0.5)
+        if lk[0]:
+            re, im = f(val.real), f(val.imag)
+            zr = f(f(re * re) - f(im * im))
+            zi = f(f(re * im) + f(im * re))
+            ns = f(f(zr * zr) + f(zi * zi))
+            want[i, 1] = f(f(f(v[i] * zr) / ns) * f(0.5))
+    assert (want[:, 1] != 0).sum() > 500, "the pilot PLL never locked in the test signal"
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
