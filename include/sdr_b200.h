@@ -78,6 +78,9 @@ int sdr_unpack_u8iq_dev(const uint8_t *iq, size_t n_samples, float *out_c64, int
  * The handle carries the last K-1 inputs and the decimation phase across calls, so feeding a
  * stream in blocks of any size gives the same samples as one call.
  * ====================================================================================== */
+/* Default (flags = 0) for u8 IQ input is the integer tcgen05 path: taps are quantised to 24-bit fixed point relative to
+ * the largest |tap| (a tap below 2^-24 of the largest contributes nothing; error < 1e-6 of max|y|).
+ * STRICT_ORDER selects the reference-order CUDA-core kernel instead. */
 #define SDR_FIR_STRICT_ORDER 1u /* f32 mul then add, k ascending, no FMA: bit-identical to Fir::apply */
 #define SDR_FIR_NO_TENSOR 2u    /* never take a tensor-core path */
 #define SDR_FIR_NO_TCGEN05 4u   /* never take the tcgen05/TMEM path (the mma.sync Toeplitz path may still run) */
@@ -136,7 +139,8 @@ size_t sdr_block_samples(float size, float rate);
 #define SDR_FFT_RFFT 4u
 
 typedef struct {
-    size_t n;          /* transform length, any n >= 1 */
+    size_t n;          /* transform length: any n >= 1 up to 2^27 (powers of two) or 2^26 (any other length,
+                        * Bluestein); SDR_ERR_UNSUPPORTED beyond.  fft::fft takes a whole finite signal */
     int input_format;  /* U8IQ, C64, or F32 (with SDR_FFT_RFFT) */
     unsigned flags;
     int device;
@@ -290,6 +294,10 @@ int sdr_src_reset(SDR_SRC_STATE *);
 SDR_SRC_STATE *sdr_src_clone(SDR_SRC_STATE *, int *error);
 int sdr_src_set_ratio(SDR_SRC_STATE *, double new_ratio);
 int sdr_src_get_channels(SDR_SRC_STATE *);
+/* frames of input history the handle carries between calls (sinc converters: bounded by the filter
+ * wing + what the last call consumed; a call that stops at `output_frames` hands the input it did
+ * not need back through input_frames_used, as libsamplerate's src_process does) */
+long sdr_src_history_frames(SDR_SRC_STATE *);
 const char *sdr_src_strerror(int error);
 const char *sdr_src_get_name(int converter_type);        /* resample.rs:125 */
 const char *sdr_src_get_description(int converter_type); /* resample.rs:133 */
@@ -332,7 +340,9 @@ sdr_fm_t *sdr_fm_create(const sdr_fm_config_t *cfg, int *err);
 void sdr_fm_destroy(sdr_fm_t *);
 int sdr_fm_reset(sdr_fm_t *);
 float sdr_fm_output_rate(const sdr_fm_t *);          /* 48000 */
-size_t sdr_fm_max_output(const sdr_fm_t *, size_t n); /* an out_cap that is always enough for n input samples */
+/* the out_cap sdr_fm_process[_dev] requires for n input samples: a smaller one is rejected with
+ * SDR_ERR_OUTPUT_TOO_SMALL before any state changes (the call can be retried with a larger buffer) */
+size_t sdr_fm_max_output(const sdr_fm_t *, size_t n);
 /* iq: n_stations rows of n u8 IQ samples (2n bytes each, row stride in_stride BYTES);
  * out: n_stations rows of (left, right) f32 frames at 48 kHz, capacity out_cap frames per row,
  * row stride out_stride frames; *n_out = frames written per row (the same for every station).

@@ -596,7 +596,8 @@ extern "C" size_t orc_freq_sweep(float rate, float df, int warmup, float rs, flo
 //     last_value initialisation).
 //   * Sinc*: y = rho * sum_j coef(|j - T| * rho * Q) * x[j], rho = min(ratio, 1), coefficient by
 //     linear interpolation in a half-table with Q entries per zero crossing, f64 accumulation,
-//     left wing far->near then right wing far->near; no group delay (output m at T = m*step);
+//     left wing far->near then right wing far->near; no group delay (output m at T = m*step); a call that stops at
+//     output_frames consumes only the input its outputs and the next output's window need;
 //     outputs stop when T + step > total input length once end_of_input was signalled.
 // Deliberate divergences from libsamplerate (documented in DESIGN.md): closed-form positions
 // P + m*step instead of a running fmod accumulation (identical whenever step is exactly
@@ -719,6 +720,10 @@ extern "C" int orc_src_set_ratio(orc_src_t *s, double r) {
     return 0;
 }
 extern "C" int orc_src_get_channels(const orc_src_t *s) { return s ? s->channels : -ORC_ERR_BAD_STATE; }
+extern "C" long orc_src_history_frames(const orc_src_t *s) {
+    if (!s) return -ORC_ERR_BAD_STATE;
+    return (s->type == ORC_SRC_ZERO_ORDER_HOLD || s->type == ORC_SRC_LINEAR) ? (s->fresh ? 0 : 1) : (long)(s->buf.size() / s->channels);
+}
 extern "C" const char *orc_src_strerror(int e) {
     switch (e) {
         case 0: return "No error.";
@@ -787,19 +792,18 @@ static int process_sinc(orc_src *s, orc_src_data_t *d) {
     const double rq = rho * (double)sp.increment;         // table entries per input frame
     const double wing = (double)sp.half_len / rq;         // half width in input frames
     const long wc = (long)std::ceil(wing);
-    // take all offered input (libsamplerate copies input into its own ring the same way)
+    // all offered input is visible to this call's outputs; how much of it is CONSUMED is decided below
+    const long kept = (long)(s->buf.size() / ch);
     s->buf.insert(s->buf.end(), d->data_in, d->data_in + (size_t)n * ch);
-    s->total_in += n;
-    d->input_frames_used = n;
-    if (d->end_of_input) s->ended = true;
-    const long have = (long)(s->buf.size() / ch);
-    const double end_rel = (double)(s->total_in - s->buf_origin);  // one past the last real frame
+    const bool ending = s->ended || d->end_of_input;
+    long have = (long)(s->buf.size() / ch);
+    const double end_rel = (double)(s->total_in + n - s->buf_origin);  // one past the last real frame
     long m = 0;
     const double P = s->spos;
     while (m < cap) {
         const double T = P + (double)m * step;
         const long i0 = (long)std::floor(T);
-        if (s->ended) {
+        if (ending) {
             if (T + step > end_rel) break;
         } else {
             if (i0 + wc + 1 > have - 1) break;  // lookahead not yet available
@@ -831,6 +835,21 @@ static int process_sinc(orc_src *s, orc_src_data_t *d) {
         ++m;
     }
     d->output_frames_gen = m;
+    // Input consumption (libsamplerate consumes only what the outputs it generated needed): when the output
+    // capacity ended the call, keep just the frames the NEXT output's window reaches (index floor(Pn)+wc+1) and
+    // hand the rest back to the caller -- the carried history stays bounded for any ratio.
+    long used = n;
+    if (m == cap) {
+        const long need = (long)std::floor(P + (double)m * step) + wc + 2 - kept;
+        used = need < 0 ? 0 : (need > n ? n : need);
+    }
+    if (used < n) {
+        s->buf.resize((size_t)(kept + used) * ch);
+        have = kept + used;
+    }
+    s->total_in += used;
+    d->input_frames_used = used;
+    if (d->end_of_input && used == n) s->ended = true;
     // rebase: keep wc+2 frames behind the next output position
     const double Pn = P + (double)m * step;
     long drop = (long)std::floor(Pn) - wc - 2;

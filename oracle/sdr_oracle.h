@@ -137,6 +137,7 @@ int orc_src_reset(orc_src_t *);
 orc_src_t *orc_src_clone(const orc_src_t *, int *error);
 int orc_src_set_ratio(orc_src_t *, double ratio);
 int orc_src_get_channels(const orc_src_t *);
+long orc_src_history_frames(const orc_src_t *);
 const char *orc_src_strerror(int error);
 /* the coefficient design shared with the product (pure function of the type):
  * returns half-length (number of table entries), *increment = entries per zero crossing */

@@ -84,6 +84,7 @@ def lib():
             "orc_src_clone": (vp, [vp, vp]),
             "orc_src_set_ratio": (i, [vp, C.c_double]),
             "orc_src_get_channels": (i, [vp]),
+            "orc_src_history_frames": (C.c_long, [vp]),
             "orc_src_strerror": (C.c_char_p, [i]),
             "orc_src_sinc_table": (sz, [i, vp, vp]),
             "orc_resample_signal": (sz, [vp, sz, i, i, C.c_double, vp, sz]),
@@ -321,6 +322,9 @@ class SampleRate:
 
     def reset(self):
         return lib().orc_src_reset(self.h)
+
+    def history_frames(self):
+        return lib().orc_src_history_frames(self.h)
 
     def __del__(self):
         if getattr(self, "h", None):

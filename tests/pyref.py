@@ -134,3 +134,100 @@ def freq_sweep(rate, df, warmup, start, end):
         fr.append(freq)
         vals.append(complex(f32(1) * cosf(phase), f32(1) * sinf(phase)))
     return np.array(fr, np.float32), np.array(vals, np.complex64)
+
+
+# ---- signal::Block (src/signal/adapters/block.rs) ---------------------------------------------------
+class _Tee:
+    """TeeDequeShared (block.rs:7-11): data (newest block at index 0) + one `available` count per reader."""
+
+    def __init__(self):
+        self.data = []
+        self.available = [0]
+
+
+class BlockRef:
+    """Block::next one sample at a time (block.rs:148-203) with the rayon task run synchronously at the point it is
+    spawned (the reference's result does not depend on when the task runs as long as every pop finds its block).
+    upstream: a Python iterator of samples.  clone() = Clone for Block (:129-140) + Clone for TeeDeque (:92-103)."""
+
+    def __init__(self, upstream, rate, size, _share=None):
+        if _share is not None:
+            self.up, self.tee, self.block_size = _share
+            self.tee.available.append(len(self.tee.data))  # :95-96
+            self.id = len(self.tee.available) - 1
+        else:
+            self.up = upstream
+            self.block_size = as_usize(math.ceil(float(f32(size) * f32(rate))))  # :117
+            self.tee = _Tee()
+            self.id = 0
+        self.current = []
+        self.i = 0
+
+    def clone(self):
+        return BlockRef(None, 0, 0, _share=(self.up, self.tee, self.block_size))
+
+    def _push(self):  # TeeDequePush::push (:76-89) around the fill closure (:176-187)
+        t = self.tee
+        if max(t.available) < len(t.data):
+            t.data.pop()
+        v = []
+        for _ in range(self.block_size):
+            try:
+                v.append(next(self.up))
+            except StopIteration:
+                pass
+        t.data.insert(0, v)
+        t.available = [a + 1 for a in t.available]
+
+    def next(self):
+        if self.i < len(self.current):      # :149-152
+            r = self.current[self.i]
+            self.i += 1
+            return r
+        self.current = []                   # :154-155
+        self.i = 0
+        needs_extra = True
+        t = self.tee
+        avail = 0
+        if t.available[self.id] > 0:        # try_pop :46-58
+            t.available[self.id] -= 1
+            avail = t.available[self.id]
+            self.current = list(t.data[avail])
+            needs_extra = False
+        if avail < 1:                       # target = 1 (:165-166)
+            jobs = 1 - avail + (1 if needs_extra else 0)
+            for _ in range(jobs):
+                self._push()
+            if needs_extra:                 # pop :60-73
+                t.available[self.id] -= 1
+                self.current = list(t.data[t.available[self.id]])
+        if self.i < len(self.current):      # :197-199 -- note: i is NOT advanced
+            return self.current[self.i]
+        return None
+
+
+def pll_trace(reference, gain, loop, out, lock, rate, x):
+    """run Pll over x (complex64 array) with LowPass (freq, q) sub-filters; returns (output, locked, arg) where arg is
+    the phase detector's atan2 before the gain -- used to find where a trajectory comes near atan2's branch cut"""
+    zero2 = f32(0)
+    p = Pll(reference, gain, CBiquad(lambda: lowpass(loop[0], loop[1], rate)), lowpass(out[0], out[1], rate),
+            lowpass(lock[0], lock[1], rate), rate)
+    o = np.empty(len(x), np.float32)
+    l = np.empty(len(x), np.uint8)
+    a = np.empty(len(x), np.float32)
+    for i, v in enumerate(x):
+        vr, vi = f32(v.real), f32(v.imag)
+        o_re, o_im = p.value[0], -p.value[1]
+        c = (vr * o_re - vi * o_im, vr * o_im + vi * o_re)
+        lf = p.loopf.apply(c)
+        arg = atan2f(lf[1], lf[0])
+        a[i] = arg
+        phasedif = arg * p.gain
+        p.nphase = p.nphase + (p.reference + phasedif)
+        p.nphase = p.nphase - np.trunc(p.nphase)
+        phase = f32(2.0) * PI * p.nphase
+        p.value = (f32(1) * cosf(phase), f32(1) * sinf(phase))
+        locked = p.lockf.apply(c[0])
+        o[i] = p.outf.apply(phasedif * p.rate)
+        l[i] = 1 if locked > f32(0.01) else 0
+    return o, l, a

@@ -103,6 +103,38 @@ def test_arbitrary_length_bluestein(sdr, n):
     check(got, x, shift=True, norm=True)
 
 
+@pytest.mark.parametrize("n,batches", [(1 << 17, 2), (1 << 18, 1), (1 << 21, 1), (32769, 2), (65537, 1), (180000, 1),
+                                       (1 << 16, 3)])
+def test_whole_signal_lengths_beyond_the_single_launch_kernels(sdr, n, batches):
+    """fft::fft transforms a whole finite signal of any length (fft.rs:8): take(0.1) at 1.8 MS/s is 180 000 samples.
+    Powers of two above 2^16 take the four-step path, other lengths above 32768 Bluestein over it; the boundary
+    lengths on either side are here too."""
+    x = gen.complex_noise(batches * n, n % 1000).reshape(batches, n)
+    got = sdr.FftPlan(n, "c64", shift=True, norm=True).exec(x)
+    check(got, x, shift=True, norm=True)
+    if n == 180000:
+        raw = gen.random_u8(2 * n, 5)
+        lab, vals = sdr.signal.fft(sdr.signal.from_u8iq(1.8e6, raw).take(0.1))
+        ol, ov = O.fft_shifted(O.unpack_u8iq(raw), 1.8e6)
+        assert len(vals) == n and np.array_equal(lab, ol)
+        assert np.abs(vals - ov).max() / np.abs(ov).max() < 1e-5 * np.log2(n)
+
+
+@pytest.mark.parametrize("n", [1 << 15, 1 << 16, 1 << 17, 100000])
+def test_rfft_of_long_signals(sdr, n):
+    x = gen.noise(n, 23).astype(np.float32)
+    labels, vals = sdr.rfft(x, 144000.0)
+    assert len(vals) == n - n // 2 and np.array_equal(labels, sdr.fft_labels(n, 144000.0, rfft=True))
+    ref = np.fft.fft(x.astype(np.float64))[:n - n // 2] / np.sqrt(n)
+    assert np.abs(vals - ref).max() / np.abs(ref).max() < 1e-5 * np.log2(n)
+
+
+def test_fft_length_limit_is_reported(sdr):
+    with pytest.raises(sdr.SdrError) as e:
+        sdr.FftPlan(1 << 28, "c64")
+    assert e.value.code == 101  # SDR_ERR_UNSUPPORTED
+
+
 @pytest.mark.parametrize("n", [8, 1001, 4096, 14400])
 def test_rfft_matches_reference_semantics(sdr, n):
     x = gen.noise(n, 17).astype(np.float32)

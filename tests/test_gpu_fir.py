@@ -57,6 +57,24 @@ def test_fir_strict_c64_and_real_samples(sdr, fmt):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
 
 
+@pytest.mark.parametrize("K", [57, 61, 64, 255])
+def test_fir_strict_does_not_read_beyond_tap_k_minus_1(sdr, K):
+    """Fir::apply multiplies exactly K samples (fir.rs:27-30).  An Inf / NaN sample must poison exactly the K outputs
+    whose window holds it -- the kernel's zero padding of the tap table to a multiple of 8 must not extend that by
+    Inf * 0 = NaN."""
+    taps = gen.lowpass_taps(K, 100e3, 2.4e6)
+    x = gen.complex_noise(8192, 9)
+    x[3000] = np.inf + 0j
+    x[5000] = np.nan
+    want = O.Fir(taps).apply(x)
+    got = sdr.Fir(taps, "c64", strict=True).process(x)
+    assert np.array_equal(np.isnan(got.view(np.float32)), np.isnan(want.view(np.float32)))
+    assert np.array_equal(got.view(np.uint32)[~np.isnan(want.view(np.float32))],
+                          want.view(np.uint32)[~np.isnan(want.view(np.float32))])
+    bad = np.isnan(want.real) | np.isinf(want.real)
+    assert bad[3000:3000 + K].all() and not bad[3000 + K:5000].any()
+
+
 NO_TENSOR, NO_TCGEN05 = 2, 4  # SDR_FIR_NO_TENSOR, SDR_FIR_NO_TCGEN05
 
 

@@ -149,6 +149,14 @@ def test_fm_stereo_contract_and_edges(sdr):
     two = sdr.FmStereo(2, RATE).process(np.stack([iq, iq]), end_of_input=True)
     assert np.array_equal(two[0].view(np.uint32), two[1].view(np.uint32))
     assert np.array_equal(two[0].view(np.uint32), one.view(np.uint32))
+    # a short output buffer is refused before any state advances: the same block then goes through unchanged
+    import ctypes as C
+    fm2 = sdr.FmStereo(1, RATE)
+    small = np.empty((8, 2), np.float32)
+    got = C.c_size_t(0)
+    rc = sdr.lib().sdr_fm_process(fm2.h, iq.ctypes.data, len(iq) // 2, len(iq), small.ctypes.data, 8, 8, C.byref(got), 1)
+    assert rc == 104 and got.value == 0
+    assert np.array_equal(fm2.process(iq, end_of_input=True).view(np.uint32), one.view(np.uint32))
     # zero-length stereo decode is a no-op
     des = sdr.PllDesign(19000.0, 0.0002, sdr.BiquadD.LowPass(200.0, 0.7), sdr.BiquadD.LowPass(20.0, 0.7),
                         sdr.BiquadD.LowPass(20.0, 0.7))

@@ -110,7 +110,61 @@ def test_channelizer_small(sdr):
     assert np.array_equal(np.concatenate([a[0], b[0]], 1).view(np.uint32), out.view(np.uint32))
 
 
-@pytest.mark.parametrize("typ", ["Linear", "ZeroOrderHold", "SincFastest", "SincMediumQuality"])
+def test_pll_agrees_to_1e6_of_full_scale_away_from_the_atan2_branch_cut(sdr):
+    """Where the loop-filter output stays away from the negative real axis, a last-bit difference in atan2 / sin /
+    cos cannot flip the phase detector, and the loop is contracting: GPU and oracle must then agree to 1e-6 of full
+    scale (rate * gain * pi) with identical lock flags.  (a) a locked FM signal (the per-sample restatement in
+    tests/pyref.py shows |arg| <= 1.63 rad for all 20 000 samples: no crossing anywhere); (b) the examples/pll.rs
+    sweep up to its first sample within 0.25 rad of the cut (sample 11, found with the same restatement)."""
+    import pyref
+    rate, gain = 1.8e6, 0.035
+    full = rate * gain * np.pi
+    t = np.arange(20000)
+    ph = 2 * np.pi * 30e3 * t / rate + (50e3 / 1e3) * np.sin(2 * np.pi * 1e3 * t / rate)
+    x = np.exp(1j * ph).astype(np.complex64)
+    ro, rl = O.Pll(oracle_design(), rate).apply(x)
+    po, pl_, arg = pyref.pll_trace(0.0, gain, (80000.0, 0.7), (20000.0, 0.7), (20000.0, 0.7), rate, x[:3000])
+    assert np.array_equal(po.view(np.uint32), ro[:3000].view(np.uint32))   # the restatement IS the oracle's trajectory
+    assert np.abs(arg).max() < np.pi - 0.25
+    out, lk = sdr.PllBatch([example_design(sdr)], 1, rate).process(x)
+    d = np.abs(out.astype(np.float64) - ro) / full
+    assert d.max() <= 1e-6, float(d.max())
+    assert np.array_equal(lk, rl)
+    # (b) the sweep's prefix
+    _, v = O.freq_sweep(1800000.0, 20000.0, True, -200000.0, 200000.0)
+    _, _, arg = pyref.pll_trace(0.0, gain, (80000.0, 0.7), (20000.0, 0.7), (20000.0, 0.7), rate, v[:64])
+    first = int(np.argmax(np.abs(arg) > np.pi - 0.25))
+    assert first == 11
+    so, sl = O.Pll(oracle_design(), rate).apply(v)
+    out, lk = sdr.PllBatch([example_design(sdr)], 1, rate).process(v)
+    d = np.abs(out[:first].astype(np.float64) - so[:first]) / full
+    assert d.max() <= 1e-6 and np.array_equal(lk[:first], sl[:first])
+
+
+@pytest.mark.parametrize("n_ch,n", [(128, 8192), (1024, 2048)])
+def test_channelizer_default_fir_at_c4_channel_counts(sdr, n_ch, n):
+    """C4 as bench.py runs it: the DEFAULT (non-strict) multi-channel FIR feeding the PLLs, at the per-GPU (128) and
+    whole-box (1024) channel counts, vs the oracle's per-sample channelizer.  The FIR differs from the oracle's
+    sequential f32 sum in the last bits, so the PLL bar applies (see compare_pll)."""
+    taps = gen.lowpass_taps(255, 100e3, 1.8e6)
+    t = np.arange(n)
+    f0 = (0.004 * (np.arange(n_ch) % 16) - 0.03)[:, None]
+    x = np.exp(2j * np.pi * f0 * t + 0.5j * np.sin(2 * np.pi * 0.001 * t * (1 + np.arange(n_ch)[:, None] % 3)))
+    x = (x + 0.05 * gen.complex_noise(n_ch * n, 4).reshape(n_ch, n)).astype(np.complex64)
+    ch = sdr.Channelizer(taps, example_design(sdr), n_ch, 1.8e6)
+    out, lk = ch.process(x)
+    rout, rlk = O.channelizer_mt(x, taps, oracle_design(), 1.8e6, threads=O.hardware_threads())
+    compare_pll(out, lk, rout, rlk, 1.8e6, 0.035, 1e-3, "channelizer %d" % n_ch)
+    # the FIR stage alone, same handle type and flags as the channelizer builds: north-star FIR tolerance
+    fir = sdr.Fir(taps, "c64", n_channels=n_ch)
+    y = fir.process(x)
+    sel = [0, n_ch // 2, n_ch - 1]
+    for c in sel:
+        truth = O.fir_f64(taps, x[c])
+        assert np.abs(y[c] - truth).max() / np.abs(truth).max() < 1e-5, c
+
+
+@pytest.mark.parametrize("typ", ["Linear", "ZeroOrderHold", "SincFastest", "SincMediumQuality", "SincBestQuality"])
 @pytest.mark.parametrize("ratio", [0.2, 0.08, 1.0 / 3.0, 1.5, 2.0, 48000.0 / 44100.0])
 def test_samplerate_process_matches_oracle(sdr, typ, ratio):
     ct = getattr(sdr.ConverterType, typ)
@@ -135,6 +189,53 @@ def test_samplerate_process_matches_oracle(sdr, typ, ratio):
         # f64 accumulation in identical order: equal up to the final f32 rounding
         assert np.abs(ya - yb).max() <= 1.2e-7 * max(1.0, np.abs(yb).max())
         assert (ya.view(np.uint32) != yb.view(np.uint32)).mean() < 1e-3
+
+
+@pytest.mark.parametrize("typ", ["SincBestQuality", "SincMediumQuality", "SincFastest"])
+@pytest.mark.parametrize("ratio", [0.2, 1.0 / 3.0, 0.08])
+def test_samplerate_long_single_call_matches_oracle(sdr, typ, ratio):
+    """One 262 144-frame call -- the size at which the library picks its long-call kernels (src_sinc_poly_r_kernel for
+    dyadic steps) -- against the ORACLE, including SincBestQuality, the reference's default (signal/mod.rs:83)."""
+    ct = getattr(sdr.ConverterType, typ)
+    n = 262144
+    x = gen.complex_noise(n, 31).view(np.float32).reshape(-1, 2)
+    cap = int(n * ratio) + 64
+    a, b = sdr.SampleRate(ct, 2), O.SampleRate(int(ct), 2)
+    ua, ya = a.process(ratio, x, cap)
+    ub, yb = b.process(ratio, x, cap)
+    assert ua == ub == n and len(ya) == len(yb) and len(ya) > 0.9 * n * ratio
+    ta, tb = a.process(ratio, x[:0], 8192), b.process(ratio, x[:0], 8192)   # drain (end_of_input)
+    assert ta[0] == tb[0] == 0 and len(ta[1]) == len(tb[1])
+    ya, yb = np.concatenate([ya, ta[1]]), np.concatenate([yb, tb[1]])
+    assert np.abs(ya - yb).max() <= 1.2e-7 * max(1.0, np.abs(yb).max())
+    assert (ya.view(np.uint32) != yb.view(np.uint32)).mean() < 1e-3
+
+
+@pytest.mark.parametrize("typ", ["SincFastest", "SincBestQuality"])
+@pytest.mark.parametrize("ratio", [2.0, 1.5])
+def test_samplerate_hands_unneeded_input_back_and_history_stays_bounded(sdr, typ, ratio):
+    """The adaptor's pattern (adapters/resample.rs:38-82: 4096 frames in, 4096 frames of output capacity) with
+    ratio > 1: a call that stops at output_frames consumes only what it needed (libsamplerate's src_process), so the
+    carried history stays bounded.  Counts and history equal the oracle's call by call."""
+    ct = getattr(sdr.ConverterType, typ)
+    x = gen.complex_noise(40000, 3).view(np.float32).reshape(-1, 2)
+    a, b = sdr.SampleRate(ct, 2), O.SampleRate(int(ct), 2)
+    pos, hist, ya, yb = 0, [], [], []
+    for _ in range(200):
+        chunk = x[pos:pos + 4096]
+        ua, oa = a.process(ratio, chunk, 4096)
+        ub, ob = b.process(ratio, chunk, 4096)
+        assert ua == ub and len(oa) == len(ob) and a.history_frames() == b.history_frames()
+        hist.append(a.history_frames())
+        ya.append(oa)
+        yb.append(ob)
+        pos += ua
+        if len(chunk) == 0 and len(oa) == 0:
+            break
+    assert pos == len(x) and max(hist) <= 4096 + 2 * 160 + 8
+    ya, yb = np.concatenate(ya), np.concatenate(yb)
+    assert abs(len(ya) - len(x) * ratio) <= 4
+    assert np.abs(ya - yb).max() <= 1.2e-7 * max(1.0, np.abs(yb).max())
 
 
 def test_sinc_polyphase_path_equals_per_tap_kernel_bit_for_bit(sdr):
@@ -226,6 +327,97 @@ def test_c3_chain_matches_oracle_chain(sdr):
         ref = O.resample_signal(y, otyp, float(np.float64(np.float32(48e3)) / np.float64(np.float32(240e3))))
         assert len(z) == len(ref) and abs(len(z) - n // 50) <= 2
         assert np.abs(z - ref).max() <= 2e-7 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("strict", [True, False])
+def test_c3_device_resident_chain_matches_oracle_chain(sdr, strict):
+    """Exactly bench.py's `c3chain` sequence -- Fir.process_dev (u8 IQ -> 255 taps, Decimate 10) into a device buffer,
+    SampleRate.process_dev (x0.2, SincBestQuality) out of it, nothing returning to the host in between -- against
+    the oracle's Fir::apply + Decimate + SampleRate chain.  Counts are bit-exact; with the reference-order FIR the
+    intermediate is bit-identical and the output differs by at most the final f32 rounding; with the default
+    (tcgen05) FIR both stay within the north-star 1e-5 of max magnitude."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n = 1 << 20
+    iq = gen.fm_u8(n, 2.4e6, 75e3, 1e3, 0.05, gen.BASE_SEED + 3)
+    taps = gen.lowpass_taps(255, 100e3, 2.4e6)
+    st = torch.cuda.current_stream(dev)
+    raw = torch.from_numpy(iq).to(dev)
+    n_mid = n // 10 + 1
+    mid = torch.zeros(n_mid, dtype=torch.complex64, device=dev)
+    fin = torch.zeros(n_mid // 5 + 16, dtype=torch.complex64, device=dev)
+    fir = sdr.Fir(taps, "u8iq", decimation=10, strict=strict, stream=st)
+    src = sdr.SampleRate(sdr.ConverterType.SincBestQuality, 2, stream=st)
+    got_mid = fir.process_dev(raw, n, mid, n_mid)
+    used, got_fin = src.process_dev(0.2, mid, got_mid, fin, fin.shape[0])
+    torch.cuda.synchronize()
+    x = O.unpack_u8iq(iq)
+    ref_mid = O.Fir(taps).apply(x)[9::10]
+    osr = O.SampleRate(O.SRC_SINC_BEST, 2)
+    ub, ref_fin = osr.process(0.2, ref_mid.view(np.float32).reshape(-1, 2), fin.shape[0])
+    ref_fin = ref_fin.reshape(-1).view(np.complex64)
+    assert got_mid == len(ref_mid) == n // 10 and used == ub == got_mid and got_fin == len(ref_fin)
+    y_mid = mid[:got_mid].cpu().numpy()
+    y_fin = fin[:got_fin].cpu().numpy()
+    if strict:
+        assert np.array_equal(y_mid.view(np.uint32), ref_mid.view(np.uint32))
+        assert np.abs(y_fin - ref_fin).max() <= 1.2e-7 * max(1.0, np.abs(ref_fin).max())
+    else:
+        truth = O.fir_f64(taps, x)[9::10]
+        assert np.abs(y_mid - truth).max() / np.abs(truth).max() < 1e-5
+        assert np.abs(y_fin - ref_fin).max() / np.abs(ref_fin).max() < 1e-5
+
+
+def test_signal_chain_stays_in_hbm_and_equals_the_host_hop_chain(sdr):
+    """.filter().decimate().resample() pulled with collect_dev() keeps every intermediate on the
+    device (blocks are CUDA tensors between the adaptors) and returns the same samples, bit for bit, as the same
+    chain pulled through host numpy blocks -- which test_c3_chain_matches_oracle_chain pins to the oracle."""
+    import torch
+    S = sdr.signal
+    n = 480000
+    iq = gen.fm_u8(n, 2.4e6, 75e3, 1e3, 0.05, gen.BASE_SEED + 3)
+    taps = gen.lowpass_taps(255, 100e3, 2.4e6)
+
+    def chain(src):
+        return src.filter(taps).decimate(240e3)
+
+    host = chain(S.from_u8iq(2.4e6, iq))
+    y_host = host.collect(block=50000)
+    z_host = S.from_array(240e3, y_host).resample(48e3).collect()
+    # device: bytes uploaded once, FIR+decimate -> relabel the rate (SURVEY 2.4) -> resample, all in HBM
+    ctx = S.DeviceCtx(0)
+    raw = torch.from_numpy(iq).to(ctx.device)
+    before = sdr.kernel_launch_count()
+    dec = chain(S.from_device(2.4e6, raw, raw_u8iq=True))
+    y_dev = dec.collect_dev(block=50000, ctx=ctx)
+    z_dev = S.from_device(240e3, y_dev).resample(48e3).collect_dev(ctx=ctx)
+    assert y_dev.is_cuda and z_dev.is_cuda and sdr.kernel_launch_count() > before
+    assert np.array_equal(ctx.download(y_dev).view(np.uint32), y_host.view(np.uint32))
+    assert np.array_equal(ctx.download(z_dev).view(np.uint32), z_host.view(np.uint32))
+    # and against the oracle's adaptor chain (the resampler in 4096-frame chunks, adapters/resample.rs:38-82)
+    x = O.unpack_u8iq(iq)
+    truth = O.fir_f64(taps, x)[9::10]
+    assert np.abs(y_host - truth).max() / np.abs(truth).max() < 1e-5
+    ref = O.resample_signal(y_host, O.SRC_SINC_BEST, float(np.float64(np.float32(48e3)) / np.float64(np.float32(240e3))))
+    assert len(z_host) == len(ref) and np.abs(z_host - ref).max() <= 2e-7 * max(1.0, np.abs(ref).max())
+    # a PLL behind a Block on the device path: same (value, locked) as the host path
+    g = np.load(os.path.join(GOLD, "oracle_golden.npz"))
+    f_host = S.from_array(1.8e6, g["sweep"]).filter(example_design(sdr))
+    o_host = f_host.collect()
+    f_dev = S.from_device(1.8e6, torch.from_numpy(g["sweep"]).to(ctx.device)).block(0.0002, dedup=True).filter(example_design(sdr))
+    parts, locks = [], []
+    while True:
+        b = f_dev.next_block_dev(1 << 20, ctx)
+        if b.shape[0] == 0:
+            break
+        parts.append(ctx.download(b))
+        locks.append(ctx.download(f_dev.locked))
+    assert np.array_equal(np.concatenate(parts).view(np.uint32), o_host.view(np.uint32))
+    assert np.array_equal(np.concatenate(locks), f_host.locked)
+    # fft::fft of a device-resident signal
+    lab, spec = S.fft_dev(S.from_device(240e3, y_dev[:1000]), ctx=ctx)
+    lab2, spec2 = sdr.fft(y_host[:1000], 240e3)
+    assert np.array_equal(lab, lab2) and np.array_equal(ctx.download(spec).view(np.uint32), spec2.view(np.uint32))
 
 
 @pytest.mark.parametrize("cplx", [False, True])

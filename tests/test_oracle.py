@@ -240,6 +240,42 @@ def test_src_contract_errors_and_state():
     assert used == 0 and len(out) == 0
 
 
+@pytest.mark.parametrize("typ", [O.SRC_SINC_FASTEST, O.SRC_SINC_MEDIUM])
+@pytest.mark.parametrize("ratio", [2.0, 1.5, 0.2])
+def test_src_sinc_consumes_only_needed_input_and_history_stays_bounded(typ, ratio):
+    """libsamplerate's src_process consumes only the input its generated outputs needed.  The adaptor's pattern
+    (adapters/resample.rs:38-82: 4096 frames in, 4096 frames of output capacity) with ratio > 1 must not let the
+    carried history grow; and cutting a stream by output capacity must not change a single output."""
+    x = gen.complex_noise(60000, 3).view(np.float32).reshape(-1, 2)
+    one = O.SampleRate(typ, 2)
+    u, whole = one.process(ratio, x, int(len(x) * ratio) + 64)
+    tail = one.process(ratio, x[:0], 8192)[1]
+    whole = np.concatenate([whole, tail])
+    assert u == len(x)
+    s = O.SampleRate(typ, 2)
+    pos, outs, hist = 0, [], []
+    for _ in range(400):
+        chunk = x[pos:pos + 4096]
+        used, out = s.process(ratio, chunk, 4096)
+        assert 0 <= used <= len(chunk)
+        pos += used
+        outs.append(out)
+        hist.append(s.history_frames())
+        if len(chunk) == 0 and len(out) == 0:
+            break
+    got = np.concatenate(outs)
+    assert got.shape == whole.shape
+    if ratio in (2.0, 0.2):  # step exactly representable: positions P + m*step do not depend on the cut
+        assert np.array_equal(got.view(np.uint32), whole.view(np.uint32))
+    else:                    # 1/1.5 is rounded: the re-based position differs in its last bits
+        assert np.abs(got - whole).max() < 1e-5
+    # bounded: two filter wings + one refill, independent of how long the stream is
+    bound = 2 * (O.sinc_table(typ)[2] / O.sinc_table(typ)[1] / min(ratio, 1.0) + 3) + 4096
+    assert max(hist) <= bound, (max(hist), bound)
+    if ratio > 1.0:
+        assert pos == len(x) and max(hist[len(hist) // 2:]) <= max(hist[:len(hist) // 2]) + 1
+
+
 def test_sinc_tables_are_sane():
     for typ, inc, hl in ((O.SRC_SINC_BEST, 2381, 340239), (O.SRC_SINC_MEDIUM, 491, 22438), (O.SRC_SINC_FASTEST, 128, 2464)):
         t, i, n = O.sinc_table(typ)

@@ -13,7 +13,7 @@ def test_unfused_decimate_take_skip_block(sdr):
     assert np.array_equal(s.collect(block=37), O.decimate(ramp, 10)[0])
     t = S.from_array(1000.0, ramp).skip(0.1).take(0.25)
     assert np.array_equal(t.collect(block=64), ramp[100:350])
-    b = S.from_array(1000.0, ramp).block(0.0305)
+    b = S.from_array(1000.0, ramp).block(0.0305, dedup=True)
     assert b.block_size == O.block_size(0.0305, 1000.0) == 31
     assert len(b.next_block(1 << 20)) == 31
     m = S.from_array(1000.0, ramp).map(lambda v: v * 2)
@@ -104,3 +104,111 @@ def test_rtltcp_wire_protocol_against_a_loopback_server(sdr):
     assert seen["cmds"] == b"".join(struct.pack(">BI", c, a) for c, a in
                                     [(2, 2400000), (1, 99500000), (3, 1), (4, 207), (8, 1)])
     sig.conn.close()
+
+
+def _drain(sig, n_max, pulls):
+    out = []
+    for k in pulls:
+        b = sig.next_block(k)
+        out.extend(b.tolist())
+        if len(out) >= n_max:
+            break
+    return out
+
+
+def test_block_matches_reference_semantics_sample_for_sample(sdr):
+    """signal::Block against a per-sample restatement of adapters/block.rs (tests/pyref.py BlockRef): block size
+    ceil(size * rate), the short last block, end of stream -- and the reference's quirk that the first sample of every
+    block is delivered twice (block.rs:197-199 returns current[0] without advancing i)."""
+    import pyref
+    S = sdr.signal
+    x = np.arange(1, 1001, dtype=np.float32)
+    for size in (0.0305, 0.001, 0.25, 2.0):
+        ref = pyref.BlockRef(iter(x.tolist()), 1000.0, size)
+        want = []
+        while True:
+            v = ref.next()
+            if v is None:
+                break
+            want.append(v)
+        for pulls in ((1 << 20,), (1,), (7, 1, 64)):
+            b = S.from_array(1000.0, x).block(size)
+            got = []
+            for i in range(100000):
+                blk = b.next_block(pulls[i % len(pulls)])
+                if len(blk) == 0:
+                    break
+                got.extend(blk.tolist())
+            assert got == want, (size, pulls)
+        bs = O.block_size(size, 1000.0)
+        assert len(want) == 1000 + -(-1000 // bs)  # one duplicate per block
+        clean = S.from_array(1000.0, x).block(size, dedup=True).collect(block=50)
+        assert np.array_equal(clean, x)
+
+
+def test_block_clone_is_a_tee(sdr):
+    """Clone for Block (block.rs:129-140): clones share the upstream; every reader sees every block pushed after it
+    was created, plus the blocks the deque still held when it was cloned (TeeDeque::clone, :92-103)."""
+    import pyref
+    S = sdr.signal
+    x = np.arange(1, 501, dtype=np.float32)
+    # a schedule of (reader, samples to pull); reader 1 is cloned from reader 0 after step 2, reader 2 after step 5
+    schedule = [(0, 10), (0, 25), (0, 3), (1, 40), (0, 12), (1, 5), (2, 33), (0, 50), (2, 50), (1, 100), (0, 200),
+                (2, 300), (1, 300), (0, 300), (1, 300), (2, 300)]
+    clone_at = {3: (0, 1), 6: (1, 2)}
+    ref = {0: pyref.BlockRef(iter(x.tolist()), 100.0, 0.2)}
+    got_r = {0: S.from_array(100.0, x).block(0.2)}
+    want, got = {0: [], 1: [], 2: []}, {0: [], 1: [], 2: []}
+    for step, (rid, k) in enumerate(schedule):
+        if step in clone_at:
+            src, new = clone_at[step]
+            ref[new] = ref[src].clone()
+            got_r[new] = got_r[src].clone()
+        for _ in range(k):
+            v = ref[rid].next()
+            if v is None:
+                break
+            want[rid].append(v)
+        left = k
+        while left > 0:
+            blk = got_r[rid].next_block(left)
+            if len(blk) == 0:
+                break
+            got[rid].extend(blk.tolist())
+            left -= len(blk)
+    for rid in (0, 1, 2):
+        assert got[rid] == want[rid] and len(want[rid]) > 100, rid
+    # the readers together drained the single shared upstream exactly once
+    seen0 = sorted(set(want[0]))
+    assert seen0 == x.tolist()
+
+
+def test_cpp_block_tee_matches_reference_semantics(sdr):
+    """the C++ host mirror's signal::Block (host/sdr.hpp) on the same schedule as the per-sample restatement"""
+    import os
+    import subprocess
+    import pyref
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "block_tee_test")
+    lib = os.path.dirname(sdr.LIB_PATH)
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-o", exe, exe + ".cpp", "-L" + lib, "-lsdr_b200",
+                           "-Wl,-rpath," + lib, "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64", "-lcudart"])
+    sched = [(0, 10), (0, 25), (0, 3), ("c", 0), (1, 40), (0, 12), (1, 5), ("c", 1), (2, 33), (0, 50), (2, 50), (1, 100),
+             (0, 200), (2, 300), (1, 300), (0, 300), (1, 300), (2, 300)]
+    args = [str(v) for pair in sched for v in pair]
+    out = subprocess.check_output([exe, "500", "100", "0.2", "0"] + args, text=True)
+    got = {int(l.split(":")[0]): [float(v) for v in l.split(":")[1].split()] for l in out.splitlines()}
+    ref = {0: pyref.BlockRef(iter([float(i) for i in range(1, 501)]), 100.0, 0.2)}
+    want = {}
+    for a, b in sched:
+        if a == "c":
+            ref[len(ref)] = ref[b].clone()
+            continue
+        for _ in range(b):
+            v = ref[a].next()
+            if v is None:
+                break
+            want.setdefault(a, []).append(v)
+    assert got == want
+    out = subprocess.check_output([exe, "100", "1000", "0.0305", "1", "0", "1000"], text=True)
+    assert [float(v) for v in out.split(":")[1].split()] == [float(i) for i in range(1, 101)]

@@ -157,6 +157,7 @@ extern "C" int sdr_unpack_u8iq_dev(const uint8_t *iq, size_t n, float *out, int 
     int rc = check_device(device);
     if (rc) return rc;
     DeviceGuard g(device);
+    if (!g.ok) return g.status();
     return unpack_launch(iq, n, out, (cudaStream_t)stream);
 }
 extern "C" int sdr_unpack_u8iq(const uint8_t *iq, size_t n, float *out, int device) {
@@ -165,6 +166,7 @@ extern "C" int sdr_unpack_u8iq(const uint8_t *iq, size_t n, float *out, int devi
     if (n == 0) return SDR_OK;
     if (!iq || !out) return SDR_ERR_BAD_DATA_PTR;
     DeviceGuard g(device);
+    if (!g.ok) return g.status();
     DevBuf din, dout;
     rc = din.reserve(2 * n);
     if (!rc) rc = dout.reserve(8 * n);
@@ -279,7 +281,7 @@ extern "C" sdr_fir_t *sdr_fir_create(const sdr_fir_config_t *cfg, int *err) {
     f->taps.assign(f->Kp * w, 0.0f);
     std::memcpy(f->taps.data(), cfg->taps, f->K * w * sizeof(float));
     DeviceGuard g(f->dev);
-    *err = fir_alloc(f, cfg->stream);
+    *err = g.ok ? fir_alloc(f, cfg->stream) : g.status();
     if (*err) { fir_free(f); return nullptr; }
     return f;
 }
@@ -288,6 +290,7 @@ extern "C" void sdr_fir_destroy(sdr_fir_t *f) { fir_free(f); }
 extern "C" int sdr_fir_reset(sdr_fir_t *f) {
     if (!f) return SDR_ERR_NULL_HANDLE;
     DeviceGuard g(f->dev);
+    if (!g.ok) return g.status();
     f->phase = 0;
     f->cur = 0;
     int rc = fir_fill_hist(f->d_hist[0], f->fmt, (long long)(f->n_ch * f->hist_stride), f->stream.s);
@@ -369,6 +372,7 @@ extern "C" int sdr_fir_process_dev(sdr_fir_t *f, const void *in, size_t n_in, si
     if (f->n_ch == 1) { in_stride = n_in; out_stride = no; }
     if (in_stride < n_in || out_stride < no) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(f->dev);
+    if (!g.ok) return g.status();
     int rc = fir_run_dev(f, in, n_in, in_stride, out, out_stride, no);
     if (rc) return rc;
     if (n_used) *n_used = n_in;
@@ -389,6 +393,7 @@ extern "C" int sdr_fir_process(sdr_fir_t *f, const void *in, size_t n_in, size_t
     if (f->n_ch == 1) { in_stride = n_in; out_stride = no; }
     if (in_stride < n_in || out_stride < no) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(f->dev);
+    if (!g.ok) return g.status();
     const size_t es_in = elem_bytes(f->fmt), es_out = (f->fmt == SDR_FMT_F32) ? 4 : 8;
     cudaStream_t st = f->stream.s;
     // chunks of ~32 MiB of input per channel-set, multiples of 2048*D samples so every chunk but the last keeps the
@@ -421,7 +426,13 @@ extern "C" int sdr_fir_process(sdr_fir_t *f, const void *in, size_t n_in, size_t
         if (!rc) rc = copy2d((char *)out + done_out * es_out, out_stride * es_out, bout[b]->p, ds_out * es_out, cno * es_out,
                              f->n_ch, cudaMemcpyDeviceToHost, f->pipe.down);
         if (!rc) rc = f->pipe.end_download(b);
-        if (rc) { f->pipe.drain(st); return rc; }
+        if (rc) {
+            // the chunks before this one went through (their state advance is real): say so, so the caller can resume
+            f->pipe.drain(st);
+            if (n_used) *n_used = done_in;
+            if (n_out) *n_out = done_out;
+            return rc;
+        }
         done_in += cnt;
         done_out += cno;
     }
@@ -441,15 +452,16 @@ struct sdr_fft {
     size_t n = 0;
     int fmt = 0;
     unsigned flags = 0;
-    int mode = 0;  // 0 pow2 kernels, 1 naive, 2 bluestein
+    int mode = 0;  // 0 single-launch pow2 kernels, 1 naive, 2 bluestein, 3 pow2 through convert / four-step / finish
     int log_n = 0;
     float norm = 1.0f;
-    float2 *d_tw = nullptr;     // W_n (pow2 / naive) or W_m (bluestein)
+    float2 *d_tw = nullptr;     // W_n (pow2 / naive) or W_m (bluestein), when that length is <= 2^16
+    float2 *d_tw1 = nullptr, *d_tw2 = nullptr;  // lengths above 2^16: W tables of the two four-step factors
     // bluestein
     size_t m = 0;
     int log_m = 0;
     float2 *d_chirp = nullptr, *d_bfft = nullptr;
-    DevBuf d_a1, d_a2, d_work;
+    DevBuf d_a1, d_a2, d_work, d_h1, d_h2;
     DevBuf d_in, d_out, d_in2, d_out2;
     HostPipe pipe;
 };
@@ -458,9 +470,12 @@ static void fft_free(sdr_fft *p) {
     if (!p) return;
     DeviceGuard g(p->dev);
     if (p->d_tw) cudaFree(p->d_tw);
+    if (p->d_tw1) cudaFree(p->d_tw1);
+    if (p->d_tw2) cudaFree(p->d_tw2);
     if (p->d_chirp) cudaFree(p->d_chirp);
     if (p->d_bfft) cudaFree(p->d_bfft);
-    p->d_a1.release(); p->d_a2.release(); p->d_work.release(); p->d_in.release(); p->d_out.release(); p->d_in2.release(); p->d_out2.release();
+    p->d_a1.release(); p->d_a2.release(); p->d_work.release(); p->d_h1.release(); p->d_h2.release();
+    p->d_in.release(); p->d_out.release(); p->d_in2.release(); p->d_out2.release();
     p->pipe.release();
     p->stream.release();
     delete p;
@@ -482,6 +497,41 @@ static int ilog2_exact(size_t n) {
     return (((size_t)1 << l) == n) ? l : -1;
 }
 
+constexpr int FFT_MAX_LOG = 27;  // 2^27 c64 = 1 GiB per buffer; the four-step path needs four of them
+
+// tables for a plain c64 transform of length 2^l: one table up to 2^16, the two factor tables above
+static int fft_pow2_tables(sdr_fft *p, int l) {
+    cudaStream_t st = p->stream.s;
+    if (l <= 16) return upload_twiddles(&p->d_tw, (size_t)1 << l, st);
+    const int l1 = l / 2, l2 = l - l1;
+    int rc = upload_twiddles(&p->d_tw1, (size_t)1 << l1, st);
+    if (!rc) rc = upload_twiddles(&p->d_tw2, (size_t)1 << l2, st);
+    return rc;
+}
+
+// plain forward c64 -> c64 transforms of length 2^l (4 <= l <= FFT_MAX_LOG) with the plan's tables
+static int fft_pow2_c64(sdr_fft *p, const float2 *in, float2 *out, int l, size_t batches) {
+    cudaStream_t st = p->stream.s;
+    if (l <= 16) {
+        FftArgs a;
+        a.in = in; a.out = out; a.tw = p->d_tw; a.batches = (long long)batches; a.log_n = l; a.fmt = SDR_FMT_C64;
+        a.flags = 0; a.norm = 1.0f;
+        if (l >= 13) {
+            const int rc = p->d_work.reserve((batches + 1) * sizeof(int));
+            if (rc) return rc;
+            a.work = (int *)p->d_work.p;
+        }
+        return fft_pow2_launch(a, st);
+    }
+    const size_t bytes = (batches << l) * sizeof(float2);
+    int rc = p->d_h1.reserve(bytes);
+    if (!rc) rc = p->d_h2.reserve(bytes);
+    if (!rc) rc = p->d_work.reserve(((batches << (l - l / 2)) + 1) * sizeof(int));
+    if (rc) return rc;
+    return fft_huge_launch(in, out, (float2 *)p->d_h1.p, (float2 *)p->d_h2.p, p->d_tw1, p->d_tw2, l, (long long)batches,
+                           (int *)p->d_work.p, st);
+}
+
 static int fft_plan_init(sdr_fft *p) {
     cudaStream_t st = p->stream.s;
     const size_t n = p->n;
@@ -491,18 +541,24 @@ static int fft_plan_init(sdr_fft *p) {
         p->log_n = l2;
         return upload_twiddles(&p->d_tw, n, st);
     }
+    if (l2 >= 15) {  // 2^17 and up, and rfft of 2^15 / 2^16
+        if (l2 > FFT_MAX_LOG) return SDR_ERR_UNSUPPORTED;
+        p->mode = 3;
+        p->log_n = l2;
+        return fft_pow2_tables(p, l2);
+    }
     if (n <= 64) {
         p->mode = 1;
         return upload_twiddles(&p->d_tw, n, st);
     }
-    if (n > 32768) return SDR_ERR_UNSUPPORTED;
     // Bluestein: m = smallest power of two >= 2n-1
     p->mode = 2;
     size_t m = 16;
     while (m < 2 * n - 1) m <<= 1;
     p->m = m;
     p->log_m = ilog2_exact(m);
-    int rc = upload_twiddles(&p->d_tw, m, st);
+    if (p->log_m > FFT_MAX_LOG) return SDR_ERR_UNSUPPORTED;
+    int rc = fft_pow2_tables(p, p->log_m);
     if (rc) return rc;
     std::vector<float2> chirp(n), b(m, make_float2(0.f, 0.f));
     for (size_t j = 0; j < n; ++j) {
@@ -519,10 +575,7 @@ static int fft_plan_init(sdr_fft *p) {
     SDR_CUDA_TRY(cudaMalloc(&d_b, m * sizeof(float2)));
     SDR_CUDA_TRY(cudaMemcpyAsync(p->d_chirp, chirp.data(), n * sizeof(float2), cudaMemcpyHostToDevice, st));
     SDR_CUDA_TRY(cudaMemcpyAsync(d_b, b.data(), m * sizeof(float2), cudaMemcpyHostToDevice, st));
-    FftArgs a;
-    a.in = d_b; a.out = p->d_bfft; a.tw = p->d_tw; a.batches = 1; a.log_n = p->log_m; a.fmt = SDR_FMT_C64;
-    a.flags = 0; a.norm = 1.0f;
-    rc = fft_pow2_launch(a, st);
+    rc = fft_pow2_c64(p, d_b, p->d_bfft, p->log_m, 1);
     cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(d_b);
     if (rc) return rc;
@@ -544,7 +597,7 @@ extern "C" sdr_fft_t *sdr_fft_create(const sdr_fft_config_t *cfg, int *err) {
     p->flags = cfg->flags;
     p->norm = 1.0f / sqrtf((float)cfg->n);  // fft.rs:16
     DeviceGuard g(p->dev);
-    *err = p->stream.init(cfg->stream);
+    *err = g.ok ? p->stream.init(cfg->stream) : g.status();
     if (!*err) *err = fft_plan_init(p);
     if (*err) { fft_free(p); return nullptr; }
     return p;
@@ -570,30 +623,39 @@ static int fft_run_dev(sdr_fft *p, const void *in, size_t batches, float *out) {
     }
     if (p->mode == 1)
         return fft_naive_launch(in, (float2 *)out, p->d_tw, (long long)batches, (int)p->n, p->fmt, p->flags, p->norm, st);
+    const size_t out_len = sdr_fft_output_len(p);
+    if (p->mode == 3) {
+        // convert -> plain c64 transform -> shift / norm / rfft selection, in slabs that bound the scratch footprint
+        const size_t slab = std::max<size_t>(1, std::min<size_t>(batches, ((size_t)256 << 20) / (p->n * sizeof(float2))));
+        int rc = p->d_a1.reserve(slab * p->n * sizeof(float2));
+        if (!rc) rc = p->d_a2.reserve(slab * p->n * sizeof(float2));
+        if (rc) return rc;
+        for (size_t b0 = 0; b0 < batches; b0 += slab) {
+            const size_t nb = std::min(slab, batches - b0);
+            float2 *a1 = (float2 *)p->d_a1.p, *a2 = (float2 *)p->d_a2.p;
+            rc = fft_convert_launch((const char *)in + b0 * p->n * elem_bytes(p->fmt), a1, (long long)(nb * p->n), p->fmt, st);
+            if (!rc) rc = fft_pow2_c64(p, a1, a2, p->log_n, nb);
+            if (!rc) rc = fft_finish_launch(a2, (float2 *)out + b0 * out_len, (long long)nb, (long long)p->n, p->flags, p->norm, st);
+            if (rc) return rc;
+        }
+        return SDR_OK;
+    }
     // bluestein, in slabs that bound the scratch footprint
     const size_t slab = std::max<size_t>(1, std::min<size_t>(batches, ((size_t)64 << 20) / (p->m * sizeof(float2))));
     int rc = p->d_a1.reserve(slab * p->m * sizeof(float2));
     if (!rc) rc = p->d_a2.reserve(slab * p->m * sizeof(float2));
     if (rc) return rc;
-    if (p->log_m >= 14) rc = p->d_work.reserve((slab + 1) * sizeof(int));
-    if (rc) return rc;
-    const size_t out_len = sdr_fft_output_len(p);
     for (size_t b0 = 0; b0 < batches; b0 += slab) {
         const size_t nb = std::min(slab, batches - b0);
         const char *inb = (const char *)in + b0 * p->n * elem_bytes(p->fmt);
         float2 *a1 = (float2 *)p->d_a1.p, *a2 = (float2 *)p->d_a2.p;
         rc = bluestein_pre_launch(inb, a1, p->d_chirp, (long long)nb, (int)p->n, (int)p->m, p->fmt, st);
         if (rc) return rc;
-        FftArgs a;
-        a.in = a1; a.out = a2; a.tw = p->d_tw; a.batches = (long long)nb; a.log_n = p->log_m; a.fmt = SDR_FMT_C64;
-        a.flags = 0; a.norm = 1.0f;
-        if (p->log_m >= 14) a.work = (int *)p->d_work.p;
-        rc = fft_pow2_launch(a, st);
+        rc = fft_pow2_c64(p, a1, a2, p->log_m, nb);
         if (rc) return rc;
         rc = bluestein_mul_launch(a2, p->d_bfft, (long long)nb, (int)p->m, st);
         if (rc) return rc;
-        a.in = a2; a.out = a1;
-        rc = fft_pow2_launch(a, st);
+        rc = fft_pow2_c64(p, a2, a1, p->log_m, nb);
         if (rc) return rc;
         rc = bluestein_post_launch(a1, (float2 *)out + b0 * out_len, p->d_chirp, (long long)nb, (int)p->n, (int)p->m,
                                    p->flags, p->norm, st);
@@ -607,6 +669,7 @@ extern "C" int sdr_fft_exec_dev(sdr_fft_t *p, const void *in, size_t batches, fl
     if (batches == 0) return SDR_OK;
     if (!in || !out) return SDR_ERR_BAD_DATA_PTR;
     DeviceGuard g(p->dev);
+    if (!g.ok) return g.status();
     return fft_run_dev(p, in, batches, out);
 }
 
@@ -615,6 +678,7 @@ extern "C" int sdr_fft_exec(sdr_fft_t *p, const void *in, size_t batches, float 
     if (batches == 0) return SDR_OK;
     if (!in || !out) return SDR_ERR_BAD_DATA_PTR;
     DeviceGuard g(p->dev);
+    if (!g.ok) return g.status();
     const size_t es = elem_bytes(p->fmt), out_len = sdr_fft_output_len(p);
     cudaStream_t st = p->stream.s;
     // chunks of ~32 MiB of input (at least one transform); H2D(c+1) / kernel(c) / D2H(c-1) overlap
@@ -756,7 +820,7 @@ extern "C" sdr_pll_t *sdr_pll_create(const sdr_pll_config_t *cfg, int *err) {
         if (rc) { *err = rc; delete p; return nullptr; }
     }
     DeviceGuard g(p->dev);
-    *err = pll_alloc(p, cfg->stream);
+    *err = g.ok ? pll_alloc(p, cfg->stream) : g.status();
     if (*err) { pll_free(p); return nullptr; }
     return p;
 }
@@ -764,6 +828,7 @@ extern "C" void sdr_pll_destroy(sdr_pll_t *p) { pll_free(p); }
 extern "C" int sdr_pll_reset(sdr_pll_t *p) {
     if (!p) return SDR_ERR_NULL_HANDLE;
     DeviceGuard g(p->dev);
+    if (!g.ok) return g.status();
     SDR_CUDA_TRY(cudaMemsetAsync(p->d_state, 0, p->n_streams * sizeof(PllState), p->stream.s));
     return cuda_status(cudaStreamSynchronize(p->stream.s));
 }
@@ -793,6 +858,7 @@ extern "C" int sdr_pll_process_dev(sdr_pll_t *p, const float *in, size_t n, size
     if (p->n_streams == 1) { in_stride = n; out_stride = n; }
     if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(p->dev);
+    if (!g.ok) return g.status();
     return pll_launch((const float2 *)in, (long long)n, (long long)in_stride, out, locked, (long long)out_stride,
                       p->d_params, p->n_designs == 1, p->d_state, (int)p->n_streams,
                       (p->flags & SDR_PLL_FAST_MATH) != 0, p->any_identity, p->stream.s);
@@ -806,6 +872,7 @@ extern "C" int sdr_pll_process(sdr_pll_t *p, const float *in, size_t n, size_t i
     if (p->n_streams == 1) { in_stride = n; out_stride = n; }
     if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(p->dev);
+    if (!g.ok) return g.status();
     const size_t S = p->n_streams;
     int rc = p->d_in.reserve(S * n * 8);
     if (!rc) rc = p->d_out.reserve(S * n * 4);
@@ -832,6 +899,7 @@ extern "C" int sdr_pll_stereo_decode_dev(sdr_pll_t *p, const float *v, size_t n,
     if (p->n_streams == 1) { in_stride = n; out_stride = n; }
     if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(p->dev);
+    if (!g.ok) return g.status();
     return pll_stereo_launch(v, (long long)n, (long long)in_stride, out_md, (long long)out_stride, p->d_params,
                              p->n_designs == 1, p->d_state, (int)p->n_streams, (p->flags & SDR_PLL_FAST_MATH) != 0,
                              p->stream.s);
@@ -845,6 +913,7 @@ extern "C" int sdr_pll_stereo_decode(sdr_pll_t *p, const float *v, size_t n, siz
     if (p->n_streams == 1) { in_stride = n; out_stride = n; }
     if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(p->dev);
+    if (!g.ok) return g.status();
     const size_t S = p->n_streams;
     int rc = p->d_in.reserve(S * n * 4);
     if (!rc) rc = p->d_out.reserve(S * n * 8);
@@ -864,6 +933,7 @@ extern "C" int sdr_pll_get_state(sdr_pll_t *p, size_t idx, float *nphase, float 
     if (!p) return SDR_ERR_NULL_HANDLE;
     if (idx >= p->n_streams) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(p->dev);
+    if (!g.ok) return g.status();
     PllState s;
     SDR_CUDA_TRY(cudaStreamSynchronize(p->stream.s));
     SDR_CUDA_TRY(cudaMemcpy(&s, p->d_state + idx, sizeof(s), cudaMemcpyDeviceToHost));
@@ -933,7 +1003,7 @@ extern "C" sdr_biquad_t *sdr_biquad_create(const sdr_biquad_config_t *cfg, int *
         if (rc) { *err = rc; delete b; return nullptr; }
     }
     DeviceGuard g(b->dev);
-    *err = biquad_alloc(b, cfg->stream);
+    *err = g.ok ? biquad_alloc(b, cfg->stream) : g.status();
     if (*err) { biquad_free(b); return nullptr; }
     return b;
 }
@@ -941,6 +1011,7 @@ extern "C" void sdr_biquad_destroy(sdr_biquad_t *b) { biquad_free(b); }
 extern "C" int sdr_biquad_reset(sdr_biquad_t *b) {
     if (!b) return SDR_ERR_NULL_HANDLE;
     DeviceGuard g(b->dev);
+    if (!g.ok) return g.status();
     SDR_CUDA_TRY(cudaMemsetAsync(b->d_state, 0, b->n_streams * b->W * 4 * sizeof(float), b->stream.s));
     return cuda_status(cudaStreamSynchronize(b->stream.s));
 }
@@ -968,6 +1039,7 @@ extern "C" int sdr_biquad_process_dev(sdr_biquad_t *b, const float *in, size_t n
     if (b->n_streams == 1) { in_stride = n; out_stride = n; }
     if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(b->dev);
+    if (!g.ok) return g.status();
     return biquad_launch(in, (long long)n, (long long)in_stride, out, (long long)out_stride, b->W, b->d_coef, b->d_kind,
                          b->n_designs == 1, b->d_state, (int)(b->n_streams * b->W), b->stream.s);
 }
@@ -978,6 +1050,7 @@ extern "C" int sdr_biquad_process(sdr_biquad_t *b, const float *in, size_t n, si
     if (b->n_streams == 1) { in_stride = n; out_stride = n; }
     if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(b->dev);
+    if (!g.ok) return g.status();
     const size_t S = b->n_streams, eb = 4 * (size_t)b->W;
     int rc = b->d_in.reserve(S * n * eb);
     if (!rc) rc = b->d_out.reserve(S * n * eb);
@@ -1054,6 +1127,7 @@ extern "C" int sdr_channelizer_process_dev(sdr_channelizer_t *c, const void *in,
     if (C == 1) { in_stride = n; out_stride = n; }
     if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(c->fir->dev);
+    if (!g.ok) return g.status();
     // slab: keep the c64 intermediate around 32 MiB so it lives in the 126 MB L2
     size_t slab = std::max<size_t>(2048, (((size_t)32 << 20) / (8 * C)) / 2048 * 2048);
     slab = std::min(slab, round_up(n, 8));
@@ -1084,6 +1158,7 @@ extern "C" int sdr_channelizer_process(sdr_channelizer_t *c, const void *in, siz
     if (C == 1) { in_stride = n; out_stride = n; }
     if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(c->fir->dev);
+    if (!g.ok) return g.status();
     const size_t es = elem_bytes(c->fir->fmt);
     const size_t ds = round_up(n, 8);
     int rc = c->d_in.reserve(C * ds * es);
@@ -1153,7 +1228,7 @@ extern "C" SDR_SRC_STATE *sdr_src_new_on(int type, int channels, int device, voi
     s->dev = device; s->type = type; s->channels = channels;
     src_reset_state(s);
     DeviceGuard g(device);
-    *error = s->stream.init(stream);
+    *error = g.ok ? s->stream.init(stream) : g.status();
     if (!*error && type <= SDR_SRC_SINC_FASTEST) {
         const float *tab = nullptr;
         int inc = 0;
@@ -1181,6 +1256,10 @@ extern "C" int sdr_src_set_ratio(SDR_SRC_STATE *s, double r) {
     return SDR_OK;
 }
 extern "C" int sdr_src_get_channels(SDR_SRC_STATE *s) { return s ? s->channels : -SDR_ERR_BAD_STATE; }
+extern "C" long sdr_src_history_frames(SDR_SRC_STATE *s) {
+    if (!s) return -SDR_ERR_BAD_STATE;
+    return s->type >= SDR_SRC_ZERO_ORDER_HOLD ? (s->fresh ? 0 : 1) : (long)s->kept;
+}
 extern "C" const char *sdr_src_strerror(int e) {
     if (e < 0 || (e > 22 && e < 100)) return nullptr;
     return sdr_strerror(e);
@@ -1258,6 +1337,7 @@ static int src_process_impl(sdr_src *s, SDR_SRC_DATA *d, bool dev_ptrs) {
     const long long n = d->input_frames, cap = d->output_frames;
     const double step = 1.0 / s->ratio;
     DeviceGuard g(s->dev);
+    if (!g.ok) return g.status();
     cudaStream_t st = s->stream.s;
     const cudaMemcpyKind kin = dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
     const size_t fb = (size_t)ch * sizeof(float);  // bytes per frame
@@ -1331,17 +1411,27 @@ static int src_process_impl(sdr_src *s, SDR_SRC_DATA *d, bool dev_ptrs) {
     DevBuf &V2 = s->v[s->cur];
     DevBuf &W2 = s->v[s->cur ^ 1];
     if (n > 0) SDR_CUDA_TRY(cudaMemcpyAsync((char *)V2.p + (size_t)s->kept * fb, d->data_in, (size_t)n * fb, kin, st));
-    s->total_in += n;
-    d->input_frames_used = (long)n;
-    if (d->end_of_input) s->ended = true;
-    const double end_rel = (double)(s->total_in - s->origin_abs);
+    // every offered frame is visible to this call's outputs; how many are CONSUMED is decided once m is known
+    const bool ending = s->ended || d->end_of_input;
+    const double end_rel = (double)(s->total_in + n - s->origin_abs);
     const double P = s->spos;
     m = count_outputs(cap, [&](long long mm) {
         const double T = P + (double)mm * step;
         const long long i0 = (long long)std::floor(T);
-        if (s->ended) return !(T + step > end_rel);
+        if (ending) return !(T + step > end_rel);
         return !(i0 + wc + 1 > have - 1);
     });
+    // libsamplerate consumes only the input its outputs needed: when the output capacity ended the call, keep just
+    // the frames the next output's window reaches and hand the rest back (bounded history for any ratio)
+    long long used = n;
+    if (m == cap) {
+        const long long need = (long long)std::floor(P + (double)m * step) + wc + 2 - s->kept;
+        used = need < 0 ? 0 : (need > n ? n : need);
+    }
+    const long long have_kept = s->kept + used;  // frames that stay in the handle after this call
+    s->total_in += used;
+    d->input_frames_used = (long)used;
+    if (d->end_of_input && used == n) s->ended = true;
     L.v = (const float *)V2.p; L.have = have; L.origin = 0; L.pos = P; L.n_out = m;
     L.half_len = half_len; L.rq = rq; L.rho = rho; L.wc = wc;
     float *dout = d->data_out;
@@ -1360,9 +1450,9 @@ static int src_process_impl(sdr_src *s, SDR_SRC_DATA *d, bool dev_ptrs) {
     // rebase: keep wc+2 frames behind the next output position
     const double Pn = P + (double)m * step;
     long long drop = (long long)std::floor(Pn) - wc - 2;
-    if (drop > have) drop = have;
+    if (drop > have_kept) drop = have_kept;
     if (drop > 0) {
-        const long long keep = have - drop;
+        const long long keep = have_kept - drop;
         rc = W2.reserve((size_t)std::max<long long>(keep, 1) * fb);
         if (rc) return rc;
         if (keep > 0)
@@ -1372,7 +1462,7 @@ static int src_process_impl(sdr_src *s, SDR_SRC_DATA *d, bool dev_ptrs) {
         s->origin_abs += drop;
         s->spos = Pn - (double)drop;
     } else {
-        s->kept = have;
+        s->kept = have_kept;
         s->spos = Pn;
     }
     if (!dev_ptrs) SDR_CUDA_TRY(cudaStreamSynchronize(st));
@@ -1415,11 +1505,13 @@ extern "C" void sdr_timer_destroy(sdr_timer_t *t) {
 extern "C" int sdr_timer_begin(sdr_timer_t *t) {
     if (!t) return SDR_ERR_NULL_HANDLE;
     DeviceGuard g(t->dev);
+    if (!g.ok) return g.status();
     return cuda_status(cudaEventRecord(t->a, t->st));
 }
 extern "C" int sdr_timer_end(sdr_timer_t *t, float *ms) {
     if (!t) return SDR_ERR_NULL_HANDLE;
     DeviceGuard g(t->dev);
+    if (!g.ok) return g.status();
     SDR_CUDA_TRY(cudaEventRecord(t->b, t->st));
     SDR_CUDA_TRY(cudaEventSynchronize(t->b));
     return cuda_status(cudaEventElapsedTime(ms, t->a, t->b));

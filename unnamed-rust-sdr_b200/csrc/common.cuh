@@ -26,14 +26,37 @@ inline int launch_status() { return cuda_status(cudaGetLastError()); }
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
+    cudaError_t err = cudaSuccess;
     explicit DeviceGuard(int dev) {
         if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+        if (prev != dev) {
+            err = cudaSetDevice(dev);
+            ok = (err == cudaSuccess);
+        }
     }
+    // every int-returning entry point checks this: a failed cudaSetDevice must not let the call run on the
+    // caller's current device
+    int status() const { return ok ? SDR_OK : SDR_ERR_CUDA_BASE + (int)err; }
     ~DeviceGuard() {
         if (prev >= 0) cudaSetDevice(prev);
     }
 };
+
+// SM count of the CURRENT device (launchers run under a DeviceGuard).  Cached per device ordinal; the cache entries
+// are atomics, so concurrent first calls from handles on different threads / devices are benign.
+inline int current_sm_count() {
+    static std::atomic<int> cache[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 1;
+    if (dev >= 0 && dev < 64) {
+        const int c = cache[dev].load(std::memory_order_relaxed);
+        if (c > 0) return c;
+    }
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) return 1;
+    if (dev >= 0 && dev < 64) cache[dev].store(sms, std::memory_order_relaxed);
+    return sms;
+}
 
 struct StreamRef {
     cudaStream_t s = nullptr;

@@ -311,12 +311,7 @@ int launch_w1k(const FftArgs &a, cudaStream_t st) {
     const size_t smem = w1k_smem(FMT);
     const bool shift = (a.flags & SDR_FFT_SHIFT) != 0;
     auto kern = FMT != SDR_FMT_U8IQ ? fft1024_warp_kernel<FMT, 2> : shift ? fft1024_warp_kernel<FMT, 1> : fft1024_warp_kernel<FMT, 0>;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = current_sm_count();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     long long ctas = (a.batches + W1K_WARPS - 1) / W1K_WARPS;
@@ -511,12 +506,7 @@ int launch_reg2(const FftArgs &a, cudaStream_t st) {
     auto kern = fft_reg2_kernel<LOGN, FMT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = current_sm_count();
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, PL::THREADS, smem);
     if (per_sm < 1) per_sm = 1;
@@ -732,12 +722,7 @@ int launch_l2(const FftArgs &a, cudaStream_t st) {
     auto kern = fft_l2_kernel<LOGN2, FMT>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = current_sm_count();
     int per_sm = 1;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
     if (per_sm < 1) per_sm = 1;
@@ -888,6 +873,104 @@ int fft_naive_launch(const void *in, float2 *out, const float2 *tw, long long ba
         fft_naive_kernel<SDR_FMT_C64><<<grid, 128, 0, st>>>(in, out, tw, batches, n, flags, norm);
     else
         fft_naive_kernel<SDR_FMT_F32><<<grid, 128, 0, st>>>(in, out, tw, batches, n, flags, norm);
+    count_launch();
+    return launch_status();
+}
+
+// ---- lengths beyond the single-launch kernels (n = 2^17 .. 2^27): N = N1 * N2, the textbook four-step through global
+// memory.  fft::fft transforms a WHOLE finite signal in one call (src/fft.rs:8: e.g. take(0.1) at 1.8 MS/s = 180 000
+// samples -> Bluestein with m = 2^19), so this path has to exist; it is one transform per call and not a throughput
+// target.  out[c][r] = in[r][c] * W_N^{r c} (tw_n != 0) -- a tiled transpose with the twiddle evaluated in f64
+// (sincospi of the exactly reduced r*c mod N) and rounded once, as the table twiddles of the other kernels are.
+__global__ void fft_transpose_kernel(const float2 *__restrict__ in, float2 *__restrict__ out, int rows, int cols,
+                                     long long tw_n) {
+    __shared__ float2 tile[32][33];
+    const long long boff = (long long)blockIdx.z * rows * cols;
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[j][threadIdx.x] = in[boff + (long long)r * cols + c];
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) {
+            float2 v = tile[threadIdx.x][j];
+            if (tw_n) {
+                const long long q = ((long long)r * c) % tw_n;
+                double sn, cs;
+                sincospi(-2.0 * (double)q / (double)tw_n, &sn, &cs);
+                v = cmul(v, make_float2((float)cs, (float)sn));
+            }
+            out[boff + (long long)c * rows + r] = v;
+        }
+    }
+}
+
+static int transpose_launch(const float2 *in, float2 *out, int rows, int cols, long long tw_n, long long batches,
+                            cudaStream_t st) {
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32), (unsigned)batches);
+    fft_transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(in, out, rows, cols, tw_n);
+    count_launch();
+    return launch_status();
+}
+
+int fft_huge_launch(const float2 *in, float2 *out, float2 *s1, float2 *s2, const float2 *tw1, const float2 *tw2,
+                    int log_n, long long batches, int *work, cudaStream_t st) {
+    if (log_n < 17 || log_n > 27 || batches <= 0 || batches > 65535) return SDR_ERR_UNSUPPORTED;
+    const int l1 = log_n / 2, l2 = log_n - l1;  // both in [8, 14]
+    const int N1 = 1 << l1, N2 = 1 << l2;
+    const long long N = 1LL << log_n;
+    // x viewed as [N1][N2] (n = n1 N2 + n2).  (1) s1[n2][n1] = x[n1][n2]
+    int rc = transpose_launch(in, s1, N1, N2, 0, batches, st);
+    if (rc) return rc;
+    // (2) N2 * batches transforms of length N1 over n1: s2[n2][k1]
+    FftArgs a;
+    a.in = s1; a.out = s2; a.tw = tw1; a.batches = batches * N2; a.log_n = l1; a.fmt = SDR_FMT_C64; a.flags = 0;
+    a.norm = 1.0f; a.work = (l1 >= 14) ? work : nullptr;
+    rc = fft_pow2_launch(a, st);
+    if (rc) return rc;
+    // (3) s1[k1][n2] = s2[n2][k1] * W_N^{n2 k1}
+    rc = transpose_launch(s2, s1, N2, N1, N, batches, st);
+    if (rc) return rc;
+    // (4) N1 * batches transforms of length N2 over n2: s2[k1][k2]
+    a.in = s1; a.out = s2; a.tw = tw2; a.batches = batches * N1; a.log_n = l2; a.work = (l2 >= 14) ? work : nullptr;
+    rc = fft_pow2_launch(a, st);
+    if (rc) return rc;
+    // (5) X[k1 + N1 k2] = s2[k1][k2]
+    return transpose_launch(s2, out, N1, N2, 0, batches, st);
+}
+
+// format conversion in front of / post-processing behind the multi-launch paths (same element rules as the fused kernels)
+template <int FMT>
+__global__ void fft_convert_kernel(const void *in, float2 *a, long long total) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < total) a[gid] = load_elem<FMT>(in, gid);
+}
+__global__ void fft_finish_kernel(const float2 *a, float2 *out, long long batches, long long n, unsigned flags, float norm) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long out_len = (flags & SDR_FFT_RFFT) ? n - n / 2 : n;
+    if (gid >= batches * out_len) return;
+    const long long b = gid / out_len, j = gid % out_len;
+    long long k = j;
+    // fft.rs:18-25: out[i] = X[(i - n/2) mod n]; rfft drops the first n/2 of those, leaving bins 0 .. n - n/2 - 1
+    if (!(flags & SDR_FFT_RFFT) && (flags & SDR_FFT_SHIFT)) { k = j - n / 2; if (k < 0) k += n; }
+    float2 v = a[b * n + k];
+    if (flags & SDR_FFT_NORM) { v.x *= norm; v.y *= norm; }
+    out[gid] = v;
+}
+int fft_convert_launch(const void *in, float2 *a, long long total, int fmt, cudaStream_t st) {
+    const unsigned grid = (unsigned)((total + 255) / 256);
+    if (fmt == SDR_FMT_U8IQ) fft_convert_kernel<SDR_FMT_U8IQ><<<grid, 256, 0, st>>>(in, a, total);
+    else if (fmt == SDR_FMT_C64) fft_convert_kernel<SDR_FMT_C64><<<grid, 256, 0, st>>>(in, a, total);
+    else fft_convert_kernel<SDR_FMT_F32><<<grid, 256, 0, st>>>(in, a, total);
+    count_launch();
+    return launch_status();
+}
+int fft_finish_launch(const float2 *a, float2 *out, long long batches, long long n, unsigned flags, float norm,
+                      cudaStream_t st) {
+    const long long out_len = (flags & SDR_FFT_RFFT) ? n - n / 2 : n;
+    fft_finish_kernel<<<(unsigned)((batches * out_len + 255) / 256), 256, 0, st>>>(a, out, batches, n, flags, norm);
     count_launch();
     return launch_status();
 }

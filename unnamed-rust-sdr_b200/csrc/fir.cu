@@ -199,6 +199,9 @@ __global__ void __launch_bounds__(RB_THREADS, 2) fir_rb_kernel(FirArgs a) {
         }
 #pragma unroll
         for (int kk = 0; kk < 8; ++kk) {
+            // reference order: Fir::apply never reads beyond tap K-1 (fir.rs:27-30); the zero padding up to Kp would
+            // turn an Inf / NaN sample just outside the window into NaN (Inf * 0) on up to 7 outputs
+            if (STRICT && 8 * kc + kk >= a.K) break;
 #pragma unroll
             for (int o = 0; o < RB_O; ++o) mac<TC, STRICT>(acc[o], w[8 + o - kk], cr[kk], ci[kk]);
         }

@@ -332,12 +332,7 @@ int fir_tc_launch(const FirArgs &f, bool tc, const uint2 *d_tables, float out_sc
     a.a0_mod = (int)d;
     const size_t tab_words = (size_t)KS * NT * NTL * TCF_SPLITS * 32;
     a.btab = d_tables + (size_t)d * tab_words;
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = current_sm_count();
     auto smem_of = [&](int NW, int RB) -> size_t {
         const long long nchunks = (long long)(RB * 16 - 1) * NTL * f.D + 2 * KS + 1;
         return ((tab_words + 1) / 2 + (size_t)NW * 2 * (nchunks + 1)) * 16;

@@ -1184,12 +1184,7 @@ static int fir_umma_poly_launch(const FirArgs &f, const uint8_t *d_tables, const
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 3; ++j) a.magic[i][j] = magic[i][j];
     for (int j = 0; j < 3; ++j) a.sc[j] = sc[j];
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = current_sm_count();
     const long long nwork = (long long)a.ntiles * f.n_ch;
     const unsigned grid = (unsigned)std::min<long long>(nwork, sms);
     auto go = [&](auto kern) -> int {
@@ -1247,12 +1242,7 @@ int fir_umma_launch(const FirArgs &f, int R, int PC, int mode, const uint8_t *d_
     for (int i = 0; i < 2; ++i)
         for (int j = 0; j < 3; ++j) a.magic[i][j] = magic[i][j];
     for (int j = 0; j < 3; ++j) a.sc[j] = sc[j];
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
+    const int sms = current_sm_count();
     const long long nwork = (long long)a.ntiles * f.n_ch;
     const unsigned grid = (unsigned)std::min<long long>(nwork, sms);
     auto go = [&](auto kern) -> int {

@@ -83,7 +83,7 @@ extern "C" sdr_fm_t *sdr_fm_create(const sdr_fm_config_t *cfg, int *err) {
     f->ratio1 = (double)f->rate_mid / (double)f->rate;
     f->ratio2 = (double)f->rate_out / (double)f->rate_mid;
     DeviceGuard g(f->dev);
-    int rc = f->stream.init(cfg->stream);
+    int rc = g.ok ? f->stream.init(cfg->stream) : g.status();
     if (rc) { *err = rc; fm_free(f); return nullptr; }
     void *st = (void *)f->stream.s;
 
@@ -191,6 +191,9 @@ static int fm_run(sdr_fm *f, const uint8_t *d_iq, size_t n, size_t in_stride, fl
                   size_t out_stride, size_t *n_out, int end_of_input) {
     const size_t S = f->n_st;
     cudaStream_t st = f->stream.s;
+    // reject a short output buffer BEFORE any stage consumes the block: the PLLs and converters advance their state
+    // as they run, so a late SDR_ERR_OUTPUT_TOO_SMALL would drop samples and leave a handle that cannot be retried
+    if (out_cap < sdr_fm_max_output(f, n)) return SDR_ERR_OUTPUT_TOO_SMALL;
     const size_t cap2 = (size_t)std::ceil((double)n * f->ratio1) + kFmSlack;
     const size_t cap3 = (size_t)std::ceil((double)cap2 * f->ratio2) + kFmSlack;
     const size_t nc = (n + 1) & ~(size_t)1;  // c64 row pitch: keeps every row 16-byte aligned for the unpack kernel
@@ -238,6 +241,7 @@ extern "C" int sdr_fm_process_dev(sdr_fm_t *f, const uint8_t *iq, size_t n, size
     if (in_stride < 2 * n || out_stride < out_cap) return SDR_ERR_INVALID_ARG;
     if (f->n_st > 1 && (in_stride & 15)) return SDR_ERR_MISALIGNED;  // rows feed a 16-byte vectorised unpack
     DeviceGuard g(f->dev);
+    if (!g.ok) return g.status();
     return fm_run(f, iq, n, in_stride, out, out_cap, out_stride, n_out, end_of_input);
 }
 
@@ -248,6 +252,7 @@ extern "C" int sdr_fm_process(sdr_fm_t *f, const uint8_t *iq, size_t n, size_t i
     if (f->n_st == 1) { in_stride = 2 * n; out_stride = out_cap; }
     if (in_stride < 2 * n || out_stride < out_cap) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(f->dev);
+    if (!g.ok) return g.status();
     const size_t S = f->n_st;
     cudaStream_t st = f->stream.s;
     const size_t row = (2 * n + 15) & ~(size_t)15;  // 16-byte aligned rows for the unpack kernel

@@ -64,6 +64,14 @@ int fft_pow2_launch(const FftArgs &a, cudaStream_t st);
 // direct O(n^2) DFT for tiny / odd sizes handled without Bluestein (n <= 64)
 int fft_naive_launch(const void *in, float2 *out, const float2 *tw, long long batches, int n, int fmt,
                      unsigned flags, float norm, cudaStream_t st);
+// n = 2^17 .. 2^27, plain c64 -> c64, N = N1 * N2 through two n-element scratch buffers (five launches); tw1 / tw2 are
+// the W tables of lengths 2^(log_n / 2) and 2^(log_n - log_n / 2)
+int fft_huge_launch(const float2 *in, float2 *out, float2 *s1, float2 *s2, const float2 *tw1, const float2 *tw2,
+                    int log_n, long long batches, int *work, cudaStream_t st);
+// input format -> c64 ; c64 spectrum -> shift / norm / rfft selection of fft.rs:14-26,34-36
+int fft_convert_launch(const void *in, float2 *a, long long total, int fmt, cudaStream_t st);
+int fft_finish_launch(const float2 *a, float2 *out, long long batches, long long n, unsigned flags, float norm,
+                      cudaStream_t st);
 // Bluestein helpers: a[j] = x[j] * chirp[j] (zero padded to m), and the final pointwise stage
 int bluestein_pre_launch(const void *in, float2 *a, const float2 *chirp, long long batches, int n, int m,
                          int fmt, cudaStream_t st);

@@ -350,8 +350,10 @@ __global__ void __launch_bounds__(64) pll_kernel(const float2 *__restrict__ in, 
 
 // Stand-alone Biquad stream filter (biquad.rs:40-56): one lane per real sequence, [32 sequences x 32 samples]
 // tiles staged through shared memory like the PLL's.  W = 1: f32 streams; W = 2: c64 streams, lanes 2s, 2s+1 = re, im.
-__global__ void __launch_bounds__(32) biquad_kernel(const float *__restrict__ in, long long n, long long in_stride,
-                                                    float *__restrict__ out, long long out_stride, int W,
+// in / out are NOT __restrict__: the FM chain (fm.cu) runs the de-emphasis in place, which is safe because every
+// element is read once, by the lane that later writes it
+__global__ void __launch_bounds__(32) biquad_kernel(const float *in, long long n, long long in_stride,
+                                                    float *out, long long out_stride, int W,
                                                     const float *__restrict__ coef, const int *__restrict__ kind,
                                                     int coef_shared, float *__restrict__ state, int n_seq) {
     __shared__ float s_x[32][PLL_CHUNK + 1];

@@ -85,7 +85,7 @@ extern "C" sdr_window_fft_t *sdr_window_fft_create(const sdr_window_fft_config_t
     h->D = cfg->hop;
     h->fmt = cfg->input_format;
     DeviceGuard g(h->dev);
-    int rc = h->stream.init(cfg->stream);
+    int rc = g.ok ? h->stream.init(cfg->stream) : g.status();
     if (rc) { *err = rc; wf_free(h); return nullptr; }
     sdr_fft_config_t fc;
     fc.n = h->N;
@@ -173,6 +173,7 @@ extern "C" int sdr_window_fft_process_dev(sdr_window_fft_t *h, const void *in, s
     if (!h) return SDR_ERR_NULL_HANDLE;
     if (!n_windows || (n_in > 0 && !in) || !out_c64) return SDR_ERR_BAD_DATA_PTR;
     DeviceGuard g(h->dev);
+    if (!g.ok) return g.status();
     return wf_run(h, in, n_in, out_c64, out_cap, n_windows, cudaMemcpyDeviceToDevice);
 }
 
@@ -181,6 +182,7 @@ extern "C" int sdr_window_fft_process(sdr_window_fft_t *h, const void *in, size_
     if (!h) return SDR_ERR_NULL_HANDLE;
     if (!n_windows || (n_in > 0 && !in) || !out_c64) return SDR_ERR_BAD_DATA_PTR;
     DeviceGuard g(h->dev);
+    if (!g.ok) return g.status();
     const size_t nw = sdr_window_fft_output_count(h, n_in);
     if (nw > out_cap) return SDR_ERR_OUTPUT_TOO_SMALL;
     int rc = h->d_out.reserve(std::max<size_t>(nw * h->N * 8, 16));

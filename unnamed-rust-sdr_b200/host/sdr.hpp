@@ -23,6 +23,7 @@
 #pragma once
 #include <complex>
 #include <cstdint>
+#include <deque>
 #include <functional>
 #include <memory>
 #include <optional>
@@ -491,18 +492,105 @@ class Skip : public Signal<A> {  // adapters/mod.rs:166-194
     float rate() const override { return up_->rate(); }
 };
 
+// signal::Block (adapters/block.rs:106-207).  The upstream is pulled in blocks of ceil(size * rate) samples (:117),
+// one block ahead of the reader (target = 1, :165-189); clone() is a tee (:129-140): clones share the upstream and one
+// deque of blocks with a per-reader `available` count (TeeDeque, :7-103) -- a new reader starts with available =
+// data.len(), so it also sees the blocks the deque still held.  Faithful to the reference's quirk that `next` returns
+// current[0] without advancing `i` when it moves to a new block (:197-199): the first sample of every block is
+// delivered twice unless dedup is set (a deliberate divergence).
 template <class A>
-class Block : public Signal<A> {  // adapters/block.rs:106-207: block_size = ceil(size * rate) (:117)
-    Sig<A> up_;
-    size_t block_size_;
+class Block : public Signal<A> {
+    struct Shared {
+        Sig<A> up;
+        std::deque<std::vector<A>> data;   // samples; newest block at the front
+        std::deque<std::vector<uint8_t>> raw;  // same blocks as raw rtl_tcp bytes when the upstream hands those out
+        std::vector<size_t> available{0};
+        size_t block_size = 0;
+        bool is_raw = false, dedup = false;
+        float rate = 0.0f;
+    };
+    std::shared_ptr<Shared> sh_;
+    size_t id_ = 0, i_ = 0, cur_len_ = 0;
+    std::vector<A> cur_;
+    std::vector<uint8_t> cur_raw_;
+    bool have_cur_ = false;
+
+    void push() {  // TeeDequePush::push (:76-89) around the fill closure (:176-187)
+        Shared &s = *sh_;
+        const size_t held = s.is_raw ? s.raw.size() : s.data.size();
+        if (*std::max_element(s.available.begin(), s.available.end()) < held) {
+            if (s.is_raw) s.raw.pop_back(); else s.data.pop_back();
+        }
+        if (s.is_raw) { std::vector<uint8_t> v; s.up->next_raw(s.block_size, v); s.raw.push_front(std::move(v)); }
+        else { std::vector<A> v; s.up->next_block(s.block_size, v); s.data.push_front(std::move(v)); }
+        for (auto &a : s.available) ++a;
+    }
+    void load(size_t idx) {
+        Shared &s = *sh_;
+        if (s.is_raw) { cur_raw_ = s.raw[idx]; cur_len_ = cur_raw_.size() / 2; }
+        else { cur_ = s.data[idx]; cur_len_ = cur_.size(); }
+    }
+    size_t fetch() {  // the else-branch of Block::next (:154-195)
+        Shared &s = *sh_;
+        cur_.clear(); cur_raw_.clear(); cur_len_ = 0; i_ = 0;
+        bool needs_extra = true;
+        size_t avail = 0;
+        if (s.available[id_] > 0) { avail = --s.available[id_]; load(avail); needs_extra = false; }
+        if (avail < 1) {
+            const size_t jobs = 1 - avail + (needs_extra ? 1 : 0);
+            for (size_t j = 0; j < jobs; ++j) push();
+            if (needs_extra) load(--s.available[id_]);
+        }
+        have_cur_ = true;
+        return cur_len_;
+    }
+    template <class V, class T>
+    size_t serve(size_t n, std::vector<T> &out, const V &cur, size_t per) {
+        size_t made = 0;
+        if (!have_cur_ || i_ >= cur_len_) {
+            // note: fetch() re-fills `cur`, which the caller passed by reference
+            if (fetch() == 0 || n == 0) return 0;
+            if (!sh_->dedup) { out.insert(out.end(), cur.begin(), cur.begin() + per); made = 1; }  // (:197-199)
+        }
+        const size_t k = std::min(n - made, cur_len_ - i_);
+        out.insert(out.end(), cur.begin() + per * i_, cur.begin() + per * (i_ + k));
+        i_ += k;
+        return made + k;
+    }
 
   public:
-    Block(Sig<A> up, float size) : up_(std::move(up)) { block_size_ = sdr_block_samples(size, up_->rate()); }
-    size_t block_size() const { return block_size_; }
-    size_t next_block(size_t n, std::vector<A> &out) override { return up_->next_block(block_size_ ? std::min(n, block_size_) : n, out); }
-    bool has_raw_u8iq() const override { return up_->has_raw_u8iq(); }
-    size_t next_raw(size_t n, std::vector<uint8_t> &out) override { return up_->next_raw(block_size_ ? std::min(n, block_size_) : n, out); }
-    float rate() const override { return up_->rate(); }
+    Block(Sig<A> up, float size, bool dedup = false) : sh_(std::make_shared<Shared>()) {
+        sh_->rate = up->rate();
+        sh_->block_size = sdr_block_samples(size, up->rate());
+        sh_->is_raw = up->has_raw_u8iq();
+        sh_->dedup = dedup;
+        sh_->up = std::move(up);
+    }
+    // Clone for Block (:129-140) + Clone for TeeDeque (:92-103)
+    std::shared_ptr<Block<A>> clone() const {
+        auto b = std::shared_ptr<Block<A>>(new Block<A>(*this));
+        b->cur_.clear(); b->cur_raw_.clear(); b->cur_len_ = 0; b->i_ = 0; b->have_cur_ = false;
+        Shared &s = *sh_;
+        s.available.push_back(s.is_raw ? s.raw.size() : s.data.size());
+        b->id_ = s.available.size() - 1;
+        return b;
+    }
+    size_t block_size() const { return sh_->block_size; }
+    size_t next_block(size_t n, std::vector<A> &out) override {
+        if (!sh_->is_raw) return serve(n, out, cur_, 1);
+        // raw upstream, sample consumer: unpack the served bytes (RtlTcpSignal::next, rtltcp.rs:158-164)
+        std::vector<uint8_t> b;
+        const size_t k = serve(n, b, cur_raw_, 2);
+        if (!k) return 0;
+        const size_t o = out.size();
+        out.resize(o + k);
+        if (std::is_same<A, Complex>::value)
+            check(sdr_unpack_u8iq(b.data(), k, reinterpret_cast<float *>(out.data() + o), 0), "Block::next");
+        return k;
+    }
+    bool has_raw_u8iq() const override { return sh_->is_raw; }
+    size_t next_raw(size_t n, std::vector<uint8_t> &out) override { return serve(n, out, cur_raw_, 2); }
+    float rate() const override { return sh_->rate; }
 };
 
 template <class A, class B>
@@ -535,7 +623,7 @@ template <class A> Sig<A> resample_with(Sig<A> s, resample::ConverterType typ, f
 template <class A> Sig<A> resample(Sig<A> s, float rate) { return resample_with(std::move(s), resample::ConverterType::SincBestQuality, rate); }  // mod.rs:83
 template <class A> Sig<A> take(Sig<A> s, float duration) { return std::make_shared<Take<A>>(std::move(s), duration); }
 template <class A> Sig<A> skip(Sig<A> s, float duration) { return std::make_shared<Skip<A>>(std::move(s), duration); }
-template <class A> Sig<A> block(Sig<A> s, float size) { return std::make_shared<Block<A>>(std::move(s), size); }
+template <class A> std::shared_ptr<Block<A>> block(Sig<A> s, float size, bool dedup = false) { return std::make_shared<Block<A>>(std::move(s), size, dedup); }
 template <class A, class F> auto map(Sig<A> s, F f) -> Sig<decltype(f(std::declval<A>()))> {
     using B = decltype(f(std::declval<A>()));
     return std::make_shared<Map<A, B>>(std::move(s), std::function<B(A)>(f));

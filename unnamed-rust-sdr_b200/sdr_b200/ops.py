@@ -59,6 +59,11 @@ def unpack_u8iq(iq, device=0):
     return out
 
 
+def unpack_u8iq_dev(d_iq, n, d_out, device=0, stream=None):
+    """device-resident unpack: d_iq 2n bytes, d_out n complex64, asynchronous on `stream`"""
+    check(lib().sdr_unpack_u8iq_dev(_ptr(d_iq), n, _ptr(d_out), device, _stream_ptr(stream)), "sdr_unpack_u8iq_dev")
+
+
 def decimate_wait(rate_in, rate_out):
     return lib().sdr_decimate_wait(rate_in, rate_out)
 
@@ -603,6 +608,9 @@ class SampleRate:
 
     def get_channels(self):
         return lib().sdr_src_get_channels(self.h)
+
+    def history_frames(self):
+        return lib().sdr_src_history_frames(self.h)
 
     def close(self):
         if getattr(self, "h", None):

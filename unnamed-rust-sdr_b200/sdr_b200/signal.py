@@ -10,13 +10,53 @@ stream) and the adaptors batch exactly where the reference's own chunked adaptor
     Signal::decimate(rate)       -> Decimate (fused into a preceding FIR: only kept outputs computed)
     Signal::resample[_with]      -> Resample (SampleRate on the GPU, 4096-frame chunks)
     Signal::take / skip / block / map / iter
+
+Two ways to pull a chain.  `next_block(n)` / `collect()` return numpy arrays: every adaptor hops
+through host memory, like the reference's per-sample chain.  `next_block_dev(n, ctx)` /
+`collect_dev()` keep every intermediate in HBM: blocks travel between the
+adaptors as CUDA tensors on one stream (`DeviceCtx`), the operators run through their `*_dev`
+entry points, and only the sink decides when (if ever) samples come back to the host.  Both ways
+run the same kernels on the same blocks, so they return the same samples bit for bit.
 """
+import collections
+
 import numpy as np
 
 from . import ops
 from ._ffi import FMT_C64, FMT_F32, FMT_U8IQ
 
 DEFAULT_BLOCK = 1 << 20
+
+
+class DeviceCtx:
+    """Where a device-resident chain lives: one CUDA device and one stream.  torch is used for nothing but
+    device memory and the stream handle (the arithmetic is libsdr_b200's)."""
+
+    def __init__(self, device=0, stream=None):
+        import torch
+        self.torch = torch
+        self.index = int(device)
+        self.device = torch.device("cuda", self.index)
+        self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a)
+        with self.torch.cuda.stream(self.stream):
+            return self.torch.from_numpy(a).to(self.device)
+
+    def empty(self, shape, dtype):
+        t = self.torch
+        td = {np.dtype(np.complex64): t.complex64, np.dtype(np.float32): t.float32, np.dtype(np.uint8): t.uint8}[np.dtype(dtype)]
+        with t.cuda.stream(self.stream):
+            return t.empty(shape, dtype=td, device=self.device)
+
+    def cat(self, parts):
+        with self.torch.cuda.stream(self.stream):
+            return self.torch.cat(parts)
+
+    def download(self, d):
+        self.stream.synchronize()
+        return d.cpu().numpy()
 
 
 class Signal:
@@ -26,9 +66,27 @@ class Signal:
     def next_block(self, n):
         raise NotImplementedError
 
+    def next_block_dev(self, n, ctx):
+        """at most n samples as a CUDA tensor on ctx.stream.  Default: an adaptor without a device form (e.g. a
+        numpy Map) hops through the host once; every adaptor below overrides it."""
+        return ctx.upload(self.next_block(n))
+
+    def collect_dev(self, block=DEFAULT_BLOCK, ctx=None, device=0):
+        """drain the chain without leaving HBM; returns one CUDA tensor (asynchronous on ctx.stream)"""
+        ctx = ctx or DeviceCtx(device)
+        parts = []
+        while True:
+            b = self.next_block_dev(block, ctx)
+            if b.shape[0] == 0:
+                break
+            parts.append(b)
+        if not parts:
+            return ctx.empty((0,), getattr(self, "dtype", None) or np.complex64)
+        return parts[0] if len(parts) == 1 else ctx.cat(parts)
+
     # ---- combinators (src/signal/mod.rs:18-122) ----
-    def block(self, size):
-        return Block(self, size)
+    def block(self, size, dedup=False):
+        return Block(self, size, dedup=dedup)
 
     def decimate(self, rate):
         return Decimate(self, rate)
@@ -87,6 +145,50 @@ class FromArray(Signal):
         self.pos += len(b)
         return b
 
+    def next_block_dev(self, n, ctx):
+        return ctx.upload(self.next_block(n))
+
+
+class FromDevice(Signal):
+    """a capture that already sits in HBM (a CUDA tensor of complex64 / float32 samples, or of raw rtl_tcp bytes
+    with raw_u8iq=True): the source of a chain that never touches host memory."""
+
+    def __init__(self, rate, tensor, raw_u8iq=False):
+        self._rate = np.float32(rate)
+        self.t = tensor
+        self.is_raw = bool(raw_u8iq)
+        self.dtype = np.complex64 if raw_u8iq else {"torch.complex64": np.complex64, "torch.float32": np.float32}[str(tensor.dtype)]
+        self.pos = 0  # in samples
+
+    def rate(self):
+        return self._rate
+
+    def next_raw_dev(self, n, ctx):
+        assert self.is_raw
+        b = self.t[2 * self.pos:2 * (self.pos + n)]
+        b = b[:b.shape[0] // 2 * 2]
+        self.pos += b.shape[0] // 2
+        return b
+
+    def next_block_dev(self, n, ctx):
+        if self.is_raw:
+            raw = self.next_raw_dev(n, ctx)
+            out = ctx.empty((raw.shape[0] // 2,), np.complex64)
+            if out.shape[0]:
+                ops.unpack_u8iq_dev(raw, out.shape[0], out, ctx.index, ctx.stream)
+            return out
+        b = self.t[self.pos:self.pos + n]
+        self.pos += b.shape[0]
+        return b
+
+    def next_block(self, n):
+        ctx = DeviceCtx(self.t.device.index)
+        return ctx.download(self.next_block_dev(n, ctx))
+
+    def next_raw(self, n):
+        ctx = DeviceCtx(self.t.device.index)
+        return ctx.download(self.next_raw_dev(n, ctx))
+
 
 class FromU8IQ(Signal):
     """rtl_tcp byte stream (src/rtltcp.rs:151-168).  Consumers that understand u8 IQ (Filter, fft)
@@ -113,6 +215,22 @@ class FromU8IQ(Signal):
             return np.empty(0, np.complex64)
         return ops.unpack_u8iq(raw)
 
+    def next_raw_dev(self, n, ctx):
+        return ctx.upload(self.next_raw(n))
+
+    def next_block_dev(self, n, ctx):
+        raw = self.next_raw_dev(n, ctx)
+        out = ctx.empty((raw.shape[0] // 2,), np.complex64)
+        if out.shape[0]:
+            ops.unpack_u8iq_dev(raw, out.shape[0], out, ctx.index, ctx.stream)
+        return out
+
+
+def _has_raw(sig):
+    """does this upstream hand out raw rtl_tcp bytes (so the consumer can unpack on load)?"""
+    return bool(getattr(sig, "is_raw", False)) or isinstance(sig, FromU8IQ) or \
+        (isinstance(sig, (Block, Take, Skip)) and _has_raw(sig.signal))
+
 
 def from_array(rate, samples):
     return FromArray(rate, samples)
@@ -120,6 +238,10 @@ def from_array(rate, samples):
 
 def from_u8iq(rate, iq_bytes):
     return FromU8IQ(rate, iq_bytes)
+
+
+def from_device(rate, tensor, raw_u8iq=False):
+    return FromDevice(rate, tensor, raw_u8iq)
 
 
 class Filter(Signal):
@@ -139,19 +261,20 @@ class Filter(Signal):
             taps = np.asarray(design)
             sample_real = np.dtype(getattr(signal, "dtype", np.complex64)).kind == "f"
             self.dtype = np.float32 if sample_real else np.complex64
-            self._fmt = "u8iq" if isinstance(signal, FromU8IQ) else ("f32" if sample_real else "c64")
+            self._fmt = "u8iq" if _has_raw(signal) else ("f32" if sample_real else "c64")
             self._taps = taps
         self.locked = None
 
     def rate(self):
         return self.signal.rate()
 
-    def _ensure(self):
+    def _ensure(self, ctx=None):
         if self.op is None:
+            kw = {} if ctx is None else {"device": ctx.index, "stream": ctx.stream}
             if self.kind == "fir":
-                self.op = ops.Fir(self._taps, self._fmt, decimation=self.decimation)
+                self.op = ops.Fir(self._taps, self._fmt, decimation=self.decimation, **kw)
             else:
-                self.op = self.design.design(float(self.signal.rate()))
+                self.op = self.design.design(float(self.signal.rate()), **kw)
 
     def next_block(self, n):
         self._ensure()
@@ -171,6 +294,34 @@ class Filter(Signal):
                     continue  # a short block that produced no kept output: pull again
                 return y
             out, locked = self.op.process(x)
+            self.locked = locked
+            return out
+
+    def next_block_dev(self, n, ctx):
+        """the same blocks through sdr_fir_process_dev / sdr_pll_process_dev: input and output stay in HBM"""
+        self._ensure(ctx)
+        want = n * self.decimation
+        while True:
+            if self.kind == "fir" and self._fmt == "u8iq":
+                x = self.signal.next_raw_dev(want, ctx)
+                cnt = x.shape[0] // 2
+            else:
+                x = self.signal.next_block_dev(want, ctx)
+                cnt = x.shape[0]
+            if cnt == 0:
+                return ctx.empty((0,), self.dtype)
+            x = x.contiguous()
+            if self.kind == "fir":
+                n_out = self.op.output_count(cnt)
+                y = ctx.empty((n_out,), self.dtype)
+                got = self.op.process_dev(x, cnt, y, max(n_out, 1))
+                assert got == n_out
+                if n_out == 0:
+                    continue
+                return y
+            out = ctx.empty((cnt,), np.float32)
+            locked = ctx.empty((cnt,), np.uint8)
+            self.op.process_dev(x, cnt, out, locked)
             self.locked = locked
             return out
 
@@ -209,27 +360,47 @@ class Decimate(Signal):
             if len(y):
                 return y
 
+    def next_block_dev(self, n, ctx):
+        if self.fused:
+            return self.signal.next_block_dev(n, ctx)
+        while True:
+            x = self.signal.next_block_dev(n * self.wait, ctx)
+            if x.shape[0] == 0:
+                return x
+            first = self.wait - 1 - self.phase
+            with ctx.torch.cuda.stream(ctx.stream):
+                y = x[first::self.wait].contiguous()  # a strided device copy: indexing only, no arithmetic
+            self.phase = (self.phase + x.shape[0]) % self.wait
+            if y.shape[0]:
+                return y
+
 
 class Resample(Signal):
-    """signal::Resample (src/signal/adapters/resample.rs:5-86)."""
+    """signal::Resample (src/signal/adapters/resample.rs:5-86).  buffer_size is the reference's 4096 frames (:21);
+    a larger value batches more per SampleRate::process call (identical samples whenever 1/ratio is exactly
+    representable -- the positions P + m*step do not depend on where the stream is cut)."""
 
-    def __init__(self, signal, typ, rate):
+    def __init__(self, signal, typ, rate, buffer_size=4096):
         self.signal = signal
         self._rate = np.float32(rate)
         self.dtype = getattr(signal, "dtype", np.complex64)
         self.channels = 2 if np.dtype(self.dtype).kind == "c" else 1
-        self.sr = ops.SampleRate(typ, self.channels)
+        self.typ = typ
+        self.sr = None
         self.ratio = float(np.float64(np.float32(rate)) / np.float64(np.float32(signal.rate())))  # :25
-        self.buffer_size = 4096  # :21
-        self.buffer = np.empty((0, self.channels), np.float32)
+        self.buffer_size = int(buffer_size)
+        self.buffer = None
         self.done = False
-        self.pending = np.empty(0, self.dtype)
+        self.pending = None
 
     def rate(self):
         return self._rate
 
     def _chunk(self):
         """one turn of the `while buffer_next >= buffer_resampled.len()` loop (:44-77)"""
+        if self.sr is None:
+            self.sr = ops.SampleRate(self.typ, self.channels)
+            self.buffer = np.empty((0, self.channels), np.float32)
         while True:
             need = self.buffer_size - len(self.buffer)
             if need > 0:
@@ -247,10 +418,51 @@ class Resample(Signal):
             return out.reshape(-1).view(self.dtype) if self.channels == 2 else out.reshape(-1)
 
     def next_block(self, n):
+        if self.pending is None:
+            self.pending = np.empty(0, self.dtype)
         if self.done and len(self.pending) == 0:
             return np.empty(0, self.dtype)
         while len(self.pending) == 0 and not self.done:
             self.pending = self._chunk()
+        b = self.pending[:n]
+        self.pending = self.pending[n:]
+        return b
+
+    def _chunk_dev(self, ctx):
+        """the same loop with the 4096-frame buffer and the resampled chunk in HBM (sdr_src_process_dev); only the
+        two frame counts of SRC_DATA come back to the host, as they do from libsamplerate"""
+        t = ctx.torch
+        if self.sr is None:
+            self.sr = ops.SampleRate(self.typ, self.channels, device=ctx.index, stream=ctx.stream)
+            self.buffer = ctx.empty((0, self.channels), np.float32)
+        while True:
+            need = self.buffer_size - self.buffer.shape[0]
+            if need > 0:
+                x = self.signal.next_block_dev(need, ctx)
+                if x.shape[0]:
+                    with t.cuda.stream(ctx.stream):
+                        xf = (t.view_as_real(x) if self.channels == 2 else x.reshape(-1, 1)).reshape(-1, self.channels)
+                        self.buffer = t.cat([self.buffer, xf]) if self.buffer.shape[0] else xf.contiguous()
+            n_in = self.buffer.shape[0]
+            out = ctx.empty((self.buffer_size, self.channels), np.float32)
+            used, got = self.sr.process_dev(self.ratio, self.buffer if n_in else None, n_in, out, self.buffer_size)
+            if n_in == 0 and got == 0:
+                self.done = True
+                return ctx.empty((0,), self.dtype)
+            self.buffer = self.buffer[used:]
+            if got == 0:
+                continue
+            with t.cuda.stream(ctx.stream):
+                o = out[:got]
+                return t.view_as_complex(o) if self.channels == 2 else o.reshape(-1)
+
+    def next_block_dev(self, n, ctx):
+        if self.pending is None:
+            self.pending = ctx.empty((0,), self.dtype)
+        if self.done and self.pending.shape[0] == 0:
+            return ctx.empty((0,), self.dtype)
+        while self.pending.shape[0] == 0 and not self.done:
+            self.pending = self._chunk_dev(ctx)
         b = self.pending[:n]
         self.pending = self.pending[n:]
         return b
@@ -275,6 +487,30 @@ class Take(Signal):
         self.left -= len(b)
         return b
 
+    def next_raw(self, n):
+        n = min(n, self.left)
+        if n == 0:
+            return np.empty(0, np.uint8)
+        b = self.signal.next_raw(n)
+        self.left -= len(b) // 2
+        return b
+
+    def next_block_dev(self, n, ctx):
+        n = min(n, self.left)
+        if n == 0:
+            return ctx.empty((0,), self.dtype)
+        b = self.signal.next_block_dev(n, ctx)
+        self.left -= b.shape[0]
+        return b
+
+    def next_raw_dev(self, n, ctx):
+        n = min(n, self.left)
+        if n == 0:
+            return ctx.empty((0,), np.uint8)
+        b = self.signal.next_raw_dev(n, ctx)
+        self.left -= b.shape[0] // 2
+        return b
+
 
 class Skip(Signal):
     """signal::Skip (adapters/mod.rs:166-194)."""
@@ -287,37 +523,144 @@ class Skip(Signal):
     def rate(self):
         return self.signal.rate()
 
-    def next_block(self, n):
+    def _drop(self, pull, per):
         while self.left > 0:
-            b = self.signal.next_block(min(self.left, DEFAULT_BLOCK))
-            if len(b) == 0:
-                return b
-            self.left -= len(b)
+            b = pull(min(self.left, DEFAULT_BLOCK))
+            if b.shape[0] == 0:
+                return False
+            self.left -= b.shape[0] // per
+        return True
+
+    def next_block(self, n):
+        if not self._drop(self.signal.next_block, 1):
+            return np.empty(0, self.dtype)
         return self.signal.next_block(n)
+
+    def next_raw(self, n):
+        if not self._drop(self.signal.next_raw, 2):
+            return np.empty(0, np.uint8)
+        return self.signal.next_raw(n)
+
+    def next_block_dev(self, n, ctx):
+        if not self._drop(lambda k: self.signal.next_block_dev(k, ctx), 1):
+            return ctx.empty((0,), self.dtype)
+        return self.signal.next_block_dev(n, ctx)
+
+    def next_raw_dev(self, n, ctx):
+        if not self._drop(lambda k: self.signal.next_raw_dev(k, ctx), 2):
+            return ctx.empty((0,), np.uint8)
+        return self.signal.next_raw_dev(n, ctx)
+
+
+class _TeeDeque:
+    """TeeDeque of adapters/block.rs:7-103: one deque of blocks (newest at the front), one `available` counter per
+    reader.  push (:76-89) recycles the oldest block once no reader still needs it; a reader created by clone
+    (:92-103) starts with available = data.len(), i.e. it ALSO sees the blocks still held in the deque."""
+
+    def __init__(self):
+        self.data = collections.deque()
+        self.available = [0]
+
+    def push(self, blk):
+        if max(self.available) < len(self.data):
+            self.data.pop()  # the reference re-uses this Vec's storage; the contents are overwritten
+        self.data.appendleft(blk)
+        self.available = [a + 1 for a in self.available]
+
+    def try_pop(self, rid):
+        """(:46-58) -> (block or None, blocks still available to this reader after the pop)"""
+        if self.available[rid] > 0:
+            self.available[rid] -= 1
+            i = self.available[rid]
+            return self.data[i], i
+        return None, 0
+
+    def new_reader(self):
+        self.available.append(len(self.data))
+        return len(self.available) - 1
 
 
 class Block(Signal):
-    """signal::Block (adapters/block.rs:106-207): same samples, delivered in blocks of
-    ceil(size * rate) (block.rs:117).  The reference uses it to prefetch on a thread pool; here it
-    sets the batch size that flows into the GPU operators downstream."""
+    """signal::Block (adapters/block.rs:106-207): the upstream is pulled in blocks of ceil(size * rate) samples
+    (:117), one block AHEAD of the reader (target = 1, :171-189) -- the reference fills it on a rayon task, here
+    "ahead" means the upstream's kernels for block k+1 are already queued on the stream while block k is served --
+    and `clone()` is a tee: readers share one upstream, and each sees every block pushed after it was created plus
+    the blocks the deque still held (:92-103, :129-140).
 
-    def __init__(self, signal, size):
-        self.signal = signal
-        self.block_size = ops.block_samples(float(size), float(signal.rate()))
-        self.dtype = getattr(signal, "dtype", np.complex64)
+    Faithful to a reference quirk: when a reader moves to a new block, `next` returns `current[0]` WITHOUT advancing
+    `i` (:197-199), so the first sample of every block is delivered twice (n+1 samples per n-sample block).
+    `dedup=True` delivers each sample once instead (a deliberate divergence; clones inherit it)."""
+
+    def __init__(self, signal, size, dedup=False, _share=None):
+        if _share is not None:
+            self.__dict__.update(_share)
+            self.rid = self.tee.new_reader()
+        else:
+            self.signal = signal
+            self._rate = signal.rate()
+            self.block_size = ops.block_samples(float(size), float(signal.rate()))
+            self.dtype = getattr(signal, "dtype", np.complex64)
+            self.is_raw = _has_raw(signal)
+            self.dedup = bool(dedup)
+            self.tee = _TeeDeque()
+            self.rid = 0
+        self.current = None
+        self.i = 0
+
+    def clone(self):
+        share = {k: getattr(self, k) for k in ("signal", "_rate", "block_size", "dtype", "is_raw", "dedup", "tee")}
+        return Block(None, 0.0, _share=share)
 
     def rate(self):
-        return self.signal.rate()
+        return self._rate
+
+    def _fetch(self, pull, length):
+        """the else-branch of Block::next (:156-200): try_pop, top the deque up to one block ahead, pop"""
+        blk, avail = self.tee.try_pop(self.rid)
+        needs_extra = blk is None
+        if avail < 1:
+            jobs = (1 - avail) + (1 if needs_extra else 0)
+            for _ in range(jobs):
+                self.tee.push(pull(self.block_size))  # a short or empty block at the end of the stream (:181-185)
+            if needs_extra:
+                blk, _ = self.tee.try_pop(self.rid)
+        self.current, self.i = blk, 0
+        return length(blk)
+
+    def _serve(self, n, pull, length, take, cat, empty):
+        if self.current is None or self.i >= length(self.current):
+            if self._fetch(pull, length) == 0:
+                return empty()
+            if not self.dedup:
+                # (:197-199) current[0] is returned and i stays 0: the next call returns it again
+                first = take(self.current, 0, 1)
+                rest = take(self.current, 0, min(n - 1, length(self.current)))
+                self.i = length(rest)
+                return cat([first, rest]) if length(rest) else first
+        b = take(self.current, self.i, self.i + n)
+        self.i += length(b)
+        return b
 
     def next_block(self, n):
-        return self.signal.next_block(min(n, self.block_size) if self.block_size else n)
+        return self._serve(n, self.signal.next_block, len, lambda b, a, z: b[a:z], np.concatenate,
+                           lambda: np.empty(0, self.dtype))
 
     def next_raw(self, n):
-        return self.signal.next_raw(min(n, self.block_size) if self.block_size else n)
+        return self._serve(n, self.signal.next_raw, lambda b: len(b) // 2, lambda b, a, z: b[2 * a:2 * z],
+                           np.concatenate, lambda: np.empty(0, np.uint8))
+
+    def next_block_dev(self, n, ctx):
+        return self._serve(n, lambda k: self.signal.next_block_dev(k, ctx), lambda b: b.shape[0],
+                           lambda b, a, z: b[a:z], ctx.cat, lambda: ctx.empty((0,), self.dtype))
+
+    def next_raw_dev(self, n, ctx):
+        return self._serve(n, lambda k: self.signal.next_raw_dev(k, ctx), lambda b: b.shape[0] // 2,
+                           lambda b, a, z: b[2 * a:2 * z], ctx.cat, lambda: ctx.empty((0,), np.uint8))
 
 
 class Map(Signal):
-    """signal::Map (adapters/mod.rs:139-163); f is applied to whole blocks (vectorised)."""
+    """signal::Map (adapters/mod.rs:139-163); f is applied to whole blocks (vectorised: numpy arrays on the host
+    path, CUDA tensors on the device path)."""
 
     def __init__(self, signal, f):
         self.signal, self.f = signal, f
@@ -333,6 +676,13 @@ class Map(Signal):
         out = self.f(b)
         self.dtype = out.dtype
         return out
+
+    def next_block_dev(self, n, ctx):
+        b = self.signal.next_block_dev(n, ctx)
+        if b.shape[0] == 0:
+            return b
+        with ctx.torch.cuda.stream(ctx.stream):
+            return self.f(b)
 
 
 def fft(signal):
@@ -355,6 +705,22 @@ def rfft(signal):
     return ops.rfft(signal.collect(), float(signal.rate()))
 
 
+def fft_dev(signal, ctx=None, device=0):
+    """fft::fft(signal) with the drained signal and the spectrum left in HBM: (labels on the host -- they are a
+    function of N and the rate only, fft.rs:14-24 -- , CUDA tensor of N shifted, 1/sqrt(N)-scaled bins)."""
+    ctx = ctx or DeviceCtx(device)
+    x = signal.collect_dev(ctx=ctx).contiguous()
+    n = int(x.shape[0])
+    if n == 0:
+        return np.empty(0, np.float32), ctx.empty((0,), np.complex64)
+    plan = ops.FftPlan(n, "c64", shift=True, norm=True, device=ctx.index, stream=ctx.stream)
+    out = ctx.empty((n,), np.complex64)
+    plan.exec_dev(x, 1, out)
+    ctx.stream.synchronize()  # the plan owns scratch that must outlive the launch
+    plan.close()
+    return ops.fft_labels(n, float(signal.rate())), out
+
+
 def window_spectra(signal, duration, fps, block=DEFAULT_BLOCK):
     """signal.window(duration).decimate(fps).map(|w| fft::fft(w)) of examples/live.rs:30-39 as a generator of
     (labels, spectra[n_windows, window]) per input block.  window = round(duration * rate) (adapters/mod.rs:279),
@@ -362,7 +728,7 @@ def window_spectra(signal, duration, fps, block=DEFAULT_BLOCK):
     rate = float(signal.rate())
     window = ops.duration_samples(rate, duration)
     hop = ops.decimate_wait(rate, fps)
-    raw = hasattr(signal, "next_raw")
+    raw = _has_raw(signal)
     wf = ops.WindowFft(window, hop, "u8iq" if raw else "c64")
     labels = ops.fft_labels(window, rate)
     try:
