@@ -110,10 +110,13 @@ def test_channelizer_small(sdr):
     assert np.array_equal(np.concatenate([a[0], b[0]], 1).view(np.uint32), out.view(np.uint32))
 
 
-def test_pll_agrees_to_1e6_of_full_scale_away_from_the_atan2_branch_cut(sdr):
+def test_pll_agrees_to_phase_ulps_away_from_the_atan2_branch_cut(sdr):
     """Where the loop-filter output stays away from the negative real axis, a last-bit difference in atan2 / sin /
-    cos cannot flip the phase detector, and the loop is contracting: GPU and oracle must then agree to 1e-6 of full
-    scale (rate * gain * pi) with identical lock flags.  (a) a locked FM signal (the per-sample restatement in
+    cos cannot flip the phase detector, and the loop is contracting: GPU and oracle must then agree to a few ulps of
+    the f32 phase accumulator, with identical lock flags.  One ulp of nphase (2^-24 cycles) is 1.2e-7 of full scale
+    (rate * gain * pi) at the output, and the loop forgets a perturbation over ~1/gain = 29 samples, so differences in
+    the last bit of sin / cos / atan2 random-walk up to ~30 ulps: bar = 1e-5 of full scale for every sample and 1e-6
+    for the median (measured on B200: max 3.6e-6).  (a) a locked FM signal (the per-sample restatement in
     tests/pyref.py shows |arg| <= 1.63 rad for all 20 000 samples: no crossing anywhere); (b) the examples/pll.rs
     sweep up to its first sample within 0.25 rad of the cut (sample 11, found with the same restatement)."""
     import pyref
@@ -128,7 +131,7 @@ def test_pll_agrees_to_1e6_of_full_scale_away_from_the_atan2_branch_cut(sdr):
     assert np.abs(arg).max() < np.pi - 0.25
     out, lk = sdr.PllBatch([example_design(sdr)], 1, rate).process(x)
     d = np.abs(out.astype(np.float64) - ro) / full
-    assert d.max() <= 1e-6, float(d.max())
+    assert d.max() <= 1e-5 and np.median(d) <= 1e-6, (float(d.max()), float(np.median(d)))
     assert np.array_equal(lk, rl)
     # (b) the sweep's prefix
     _, v = O.freq_sweep(1800000.0, 20000.0, True, -200000.0, 200000.0)
@@ -352,7 +355,7 @@ def test_c3_device_resident_chain_matches_oracle_chain(sdr, strict):
     used, got_fin = src.process_dev(0.2, mid, got_mid, fin, fin.shape[0])
     torch.cuda.synchronize()
     x = O.unpack_u8iq(iq)
-    ref_mid = O.Fir(taps).apply(x)[9::10]
+    ref_mid = np.ascontiguousarray(O.Fir(taps).apply(x)[9::10])
     osr = O.SampleRate(O.SRC_SINC_BEST, 2)
     ub, ref_fin = osr.process(0.2, ref_mid.view(np.float32).reshape(-1, 2), fin.shape[0])
     ref_fin = ref_fin.reshape(-1).view(np.complex64)
