@@ -50,6 +50,8 @@ except Exception:
     pass
 
 SEED = 0x5D12B200
+FIR_C64 = {"fir255_c64": (255, 0), "fir64_c64": (64, 0), "fir255_c64_split2": (255, 16), "fir64_c64_split2": (64, 16),
+           "fir255_c64_cuda": (255, 2), "fir64_c64_cuda": (64, 2)}
 
 
 def measured_peaks():
@@ -125,10 +127,14 @@ def config_dict(name):
         "fir255_u8": ("fir255_d1_u8iq_2p26", "fused u8-IQ unpack + 255-tap real FIR, decimation 1", 1 << 26),
         "c3chain": ("c3_chain_fir255_d10_sincbest_2p26", "u8 IQ -> 255-tap FIR /10 -> SampleRate x0.2 (sincbest), device resident", 1 << 26),
         "c4": ("c4_channelizer_128ch_2p16", "128 channels x (255-tap FIR + PLL)", 128 << 16),
-        "c4_1024": ("c4_channelizer_1024ch_2p14", "1024 channels x (255-tap FIR + PLL)", 1024 << 14),
+        "c4_1024": ("c4_channelizer_1024ch_2p16", "1024 channels x (255-tap FIR + PLL), channels split over the GPUs", 1024 << 16),
     }
     alias = {"default": "c2", "fft1024_u8": "c2", "fir64_u8": "c1", "fir255_d10_u8": "c3"}
     key = alias.get(name, name)
+    if key in FIR_C64:
+        K, flags = FIR_C64[key]
+        how = {0: "tcgen05, 3 bf16 terms", 16: "tcgen05, 2 bf16 terms", 2: "CUDA cores"}[flags]
+        table[key] = ("%s_1024ch_2p16" % key, "1024 c64 channel streams x %d real taps (%s)" % (K, how), 1024 << 16)
     if key.startswith("c5_"):
         n = 1 << int(key[3:])
         wname, desc, units = "c5_fft%d_c64_2p27" % n, "batched %d-pt c64 FFT, %d transforms" % (n, (1 << 27) // n), 1 << 27
@@ -234,7 +240,7 @@ def cpu_leg(name):
         return _cpu_fir_u8(255, 1, False), 1 << 24
     if key.startswith("c5_"):
         return _cpu_fft_c64(1 << int(key[3:])), 1 << 26
-    if key.startswith("c4"):
+    if key.startswith("c4") or key in FIR_C64:
         return _cpu_channelizer, 1 << 19
     if key.startswith("fm"):
         return _cpu_fm, 1 << 19
@@ -486,6 +492,30 @@ def wl_fft_c64(cx, logn=12, log2_samples=27):
                 h2d=8 * samples, d2h=8 * samples, dtype="f32", kernel="fft", sharding="independent batches per GPU")
 
 
+def wl_fir_c64(cx, key, K=255, total_ch=1024, log2_n=16, flags=0):
+    """the FIR half of C4 alone: total_ch c64 channel streams x K real taps (Fir<f32, Complex<f32>>), channels split
+    over the ranks; flags: 0 = default (tcgen05, three bf16 terms), 16 = SDR_FIR_SPLIT2, 2 = SDR_FIR_NO_TENSOR (CUDA cores)"""
+    torch, sdr, dev = cx.torch, cx.sdr, cx.dev
+    import gen
+    n = 1 << log2_n
+    taps = gen.lowpass_taps(K, 100e3, 1.8e6)
+    clo, chi = sdr.shard.unit_range(total_ch, cx.world, cx.rank)
+    n_ch = chi - clo
+    g = torch.Generator(device=dev).manual_seed(SEED + 6 + cx.rank)
+    x = torch.view_as_complex(torch.rand((n_ch, n, 2), dtype=torch.float32, device=dev, generator=g) * 2 - 1)
+    out = torch.empty((n_ch, n), dtype=torch.complex64, device=dev)
+    fir = sdr.Fir(taps, "c64", n_channels=n_ch, flags=flags, device=dev.index, stream=cx.stream)
+
+    def step():
+        fir.process_dev(x, n, out, n, n, n)
+
+    kern = {0: "fir_umma_c64_kernel<3> (tcgen05, bf16 x 3)", 16: "fir_umma_c64_kernel<2> (tcgen05, bf16 x 2)",
+            2: "fir_rb_kernel (CUDA cores)"}.get(flags, "fir")
+    return dict(key=key, units=n_ch * n, bytes_per_unit=16.0, step=step, e2e_setup=None, e2e_step=None,
+                h2d=8 * n_ch * n, d2h=8 * n_ch * n, dtype="bf16 x bf16 -> f32 (tcgen05 kind::f16)" if flags != 2 else "f32",
+                kernel=kern, sharding="%d channels, %d per GPU (shard.unit_range)" % (total_ch, n_ch))
+
+
 def wl_channelizer(cx, key="c4", total_ch=128, log2_n=16, fast=False):
     """C4: total_ch channels split over the ranks (shard.unit_range), each channel = 255-tap FIR + PLL"""
     torch, sdr, dev = cx.torch, cx.sdr, cx.dev
@@ -578,13 +608,16 @@ def make_workload(name, cx):
     if name == "c4fast":
         return wl_channelizer(cx, "c4", 128 * cx.world, 16, fast=True)
     if name == "c4_1024":
-        return wl_channelizer(cx, "c4_1024", 1024, 14 if cx.world == 1 else 16)
+        return wl_channelizer(cx, "c4_1024", 1024, 16)
     if name.startswith("c5_"):
         return wl_fft_c64(cx, int(name[3:]))
+    if name in FIR_C64:
+        K, flags = FIR_C64[name]
+        return wl_fir_c64(cx, name, K, 1024, 16, flags)
     raise SystemExit("unknown workload " + name)
 
 
-SECONDARY = ["c1", "c1c", "c3", "c3chain", "c4_1024"] + ["c5_%d" % l for l in range(8, 17)]
+SECONDARY = ["c1", "c1c", "c3", "c3chain", "c4_1024", "fir255_c64", "fir64_c64"] + ["c5_%d" % l for l in range(8, 17)]
 
 
 def measure_config(cx, name, steps, warmup, peak):

@@ -84,6 +84,8 @@ int sdr_unpack_u8iq_dev(const uint8_t *iq, size_t n_samples, float *out_c64, int
 #define SDR_FIR_STRICT_ORDER 1u /* f32 mul then add, k ascending, no FMA: bit-identical to Fir::apply */
 #define SDR_FIR_NO_TENSOR 2u    /* never take a tensor-core path */
 #define SDR_FIR_NO_TCGEN05 4u   /* never take the tcgen05/TMEM path (the mma.sync Toeplitz path may still run) */
+#define SDR_FIR_SPLIT2 16u      /* c64 input on tcgen05: two bf16 terms per operand (3 products, error < 1e-5 of max|y|) instead of
+                                  * three (6 products, the reference's f32 accuracy); ~1.5x less tensor work */
 #define SDR_FIR_PLANAR 8u       /* real taps: tcgen05 kernel on de-interleaved I / Q byte planes (same bits; see fir_umma.cu) */
 
 typedef struct {
@@ -114,7 +116,8 @@ int sdr_fir_process(sdr_fir_t *, const void *in, size_t n_in, size_t in_stride, 
 int sdr_fir_process_dev(sdr_fir_t *, const void *in, size_t n_in, size_t in_stride, void *out,
                         size_t out_cap, size_t out_stride, size_t *n_used, size_t *n_out);
 /* which kernel family the last process call used: 0 none, 1 CUDA-core direct, 2 CUDA-core
- * strict-order, 3 tensor-core Toeplitz (mma.sync), 4 tensor-core Toeplitz (tcgen05 / TMEM, integer) */
+ * strict-order, 3 tensor-core Toeplitz (mma.sync), 4 tensor-core Toeplitz (tcgen05 / TMEM, integer, u8 IQ input),
+ * 5 tensor-core Toeplitz (tcgen05 / TMEM, bf16-split operands, c64 input with real taps) */
 int sdr_fir_last_path(const sdr_fir_t *);
 
 /* Decimate::new's `wait` = (rate_in / rate_out).round() as usize in f32 (adapters/mod.rs:22) */

@@ -75,6 +75,114 @@ def test_fir_strict_does_not_read_beyond_tap_k_minus_1(sdr, K):
     assert bad[3000:3000 + K].all() and not bad[3000 + K:5000].any()
 
 
+@pytest.mark.parametrize("K,D,tc", [(64, 1, False), (64, 1, True), (255, 10, False), (255, 7, False), (255, 3, False), (33, 1, False)])
+def test_tcgen05_path_is_alignment_invariant(sdr, K, D, tc):
+    """A stream cut across GPUs on multiples of D hands each shard an input pointer at an arbitrary even address and
+    an output pointer at an arbitrary 8-byte one.  The tcgen05 kernels must take such calls themselves (no fallback
+    to a kernel with different rounding) and return the same bits as for an aligned copy of the same samples."""
+    import torch
+    dev = torch.device("cuda", 0)
+    n = 200000
+    iq = gen.random_u8(2 * n + 64, 41)
+    taps = gen.complex_bandpass_taps(K, 200e3, 100e3, 2.048e6) if tc else gen.lowpass_taps(K, 100e3, 2.4e6)
+    base = torch.from_numpy(iq).to(dev)
+    ref = None
+    for off in (0, 2, 6, 8, 14, 30):          # bytes
+        for ooff in (0, 1):                   # complex64 elements
+            f = sdr.Fir(taps, "u8iq", decimation=D)
+            n_out = f.output_count(n)
+            out = torch.zeros(n_out + 4, dtype=torch.complex64, device=dev)
+            src = base[off:off + 2 * n] if off == 0 else base[0:2 * n].clone()
+            if off:
+                buf = torch.zeros(2 * n + 64, dtype=torch.uint8, device=dev)
+                buf[off:off + 2 * n] = base[0:2 * n]
+                src = buf[off:off + 2 * n]
+            got = f.process_dev(src, n, out[ooff:], n_out)
+            torch.cuda.synchronize()
+            assert got == n_out and f.last_path == 4, (off, ooff, f.last_path)
+            y = out[ooff:ooff + n_out].cpu().numpy()
+            if ref is None:
+                ref = y
+                truth = O.fir_f64(taps, O.unpack_u8iq(iq[:2 * n]))[D - 1::D]
+                assert np.abs(y - truth).max() / np.abs(truth).max() < 1e-5
+            else:
+                assert np.array_equal(y.view(np.uint32), ref.view(np.uint32)), (off, ooff)
+
+
+SPLIT2 = 16  # SDR_FIR_SPLIT2
+
+
+@pytest.mark.parametrize("K", [8, 33, 64, 255, 511])
+@pytest.mark.parametrize("n_ch,n", [(1, 10000), (3, 2 * 4096 + 17), (130, 5000), (2, 4096)])
+def test_tcgen05_c64_path_within_tolerance_of_f64_truth(sdr, K, n_ch, n):
+    """Fir<f32, Complex<f32>> on c64 streams (C4's multi-channel front end) on the tcgen05 Toeplitz kernel: bf16-split
+    operands, f32 accumulation in TMEM.  Default = three terms per operand: the reference's own accuracy (bar: 1.5e-6 of
+    max|y| and <= 4x the reference-order f32 error); SDR_FIR_SPLIT2 = two terms: inside the north star's 1e-5."""
+    taps = gen.lowpass_taps(K, 100e3, 1.8e6)
+    x = gen.complex_noise(n_ch * n, 100 + K).reshape(n_ch, n)
+    truth = np.stack([O.fir_f64(taps, r) for r in x])
+    ref_err = max(rel_err(O.Fir(taps).apply(x[c]), truth[c]) for c in range(min(n_ch, 3)))
+    f = sdr.Fir(taps, "c64", n_channels=n_ch)
+    y = f.process(x)
+    assert f.last_path == 5
+    err = rel_err(y, truth)
+    if K <= 384:   # three terms fit in shared memory
+        assert err < 1.5e-6 and err <= 4 * ref_err + 2e-7, (err, ref_err)
+    else:          # two terms
+        assert err < 1e-5, err
+    g = sdr.Fir(taps, "c64", n_channels=n_ch, flags=SPLIT2)
+    y2 = g.process(x)
+    assert g.last_path == 5 and rel_err(y2, truth) < 1e-5
+    # a tone well inside the passband keeps its amplitude and phase
+    t = np.arange(n)
+    tone = np.exp(2j * np.pi * 0.004 * t).astype(np.complex64)
+    yt = sdr.Fir(taps, "c64").process(tone)
+    H = np.sum(taps.astype(np.float64) * np.exp(-2j * np.pi * 0.004 * np.arange(K)))
+    assert np.abs(yt[K:] - H * tone[K:]).max() < 3e-6 * max(1.0, abs(H))
+
+
+def test_tcgen05_c64_path_streaming_impulse_and_device_pointers(sdr):
+    import torch
+    K = 255
+    taps = gen.lowpass_taps(K, 100e3, 1.8e6)
+    x = gen.complex_noise(4 * 40000, 5).reshape(4, 40000)
+    one = sdr.Fir(taps, "c64", n_channels=4).process(x)
+    # blocks that are multiples of the 4096-output tile meet the same tile grid: identical bits
+    f = sdr.Fir(taps, "c64", n_channels=4)
+    parts = [f.process(np.ascontiguousarray(x[:, a:b])) for a, b in [(0, 8192), (8192, 12288), (12288, 40000)]]
+    assert f.last_path == 5
+    assert np.array_equal(np.concatenate(parts, 1).view(np.uint32), one.view(np.uint32))
+    # ragged blocks: same samples up to the f32 accumulation order inside the tensor core
+    g = sdr.Fir(taps, "c64", n_channels=4)
+    cuts = [0, 1, 300, 5000, 5001, 20000, 40000]
+    rag = np.concatenate([g.process(np.ascontiguousarray(x[:, a:b])) for a, b in zip(cuts[:-1], cuts[1:])], 1)
+    assert np.abs(rag - one).max() <= 1e-6 * np.abs(one).max()
+    # clone mid-stream, reset
+    h = sdr.Fir(taps, "c64", n_channels=4)
+    h.process(np.ascontiguousarray(x[:, :8192]))
+    c = h.clone()
+    a1, a2 = h.process(np.ascontiguousarray(x[:, 8192:16384])), c.process(np.ascontiguousarray(x[:, 8192:16384]))
+    assert np.array_equal(a1.view(np.uint32), a2.view(np.uint32))
+    h.reset()
+    assert np.array_equal(h.process(np.ascontiguousarray(x[:, :8192])).view(np.uint32), one[:, :8192].view(np.uint32))
+    # impulse response = the taps (exactly: 1.0 has one bf16 term, the three tap terms add back to the f32 tap)
+    imp = np.zeros(1000, np.complex64)
+    imp[7] = 1.0 + 0.5j
+    yi = sdr.Fir(taps, "c64").process(imp)
+    assert np.array_equal(yi[7:7 + K].real, taps) and np.array_equal(yi[7:7 + K].imag, taps * np.float32(0.5))
+    assert np.all(yi[:7] == 0) and np.all(yi[7 + K:] == 0)
+    # device pointers at odd sample offsets (8-byte but not 16-byte aligned input): still this kernel, same tolerance
+    dev = torch.device("cuda", 0)
+    dx = torch.from_numpy(x[0]).to(dev)
+    truth = O.fir_f64(taps, x[0][3:])
+    out = torch.zeros(40000, dtype=torch.complex64, device=dev)
+    k = sdr.Fir(taps, "c64")
+    got = k.process_dev(dx[3:], 40000 - 3, out, 40000)
+    torch.cuda.synchronize()
+    assert got == 40000 - 3 and k.last_path == 5
+    assert rel_err(out[:got].cpu().numpy(), truth) < 1.5e-6
+
+
 NO_TENSOR, NO_TCGEN05 = 2, 4  # SDR_FIR_NO_TENSOR, SDR_FIR_NO_TCGEN05
 
 

@@ -192,6 +192,8 @@ struct sdr_fir {
     float *d_taps = nullptr;
     uint2 *d_tc_tables = nullptr;  // tensor-core Toeplitz tap fragments (u8 input, non-strict)
     float tc_scale = 1.0f;
+    uint8_t *d_uc_tables = nullptr;  // tcgen05 Toeplitz bf16 tap-term tables (c64 input, real taps, non-strict, D == 1)
+    int uc_ns = 0;
     uint8_t *d_um_tables = nullptr;  // tcgen05 Toeplitz digit tables (u8 input, non-strict, D == 1)
     int um_R = 0, um_PC = 0, um_planar = 0, um_magic[2][3] = {{0, 0, 0}, {0, 0, 0}};
     float um_sc[3] = {0.0f, 0.0f, 0.0f};
@@ -209,6 +211,7 @@ static void fir_free(sdr_fir *f) {
     if (f->d_taps) cudaFree(f->d_taps);
     if (f->d_tc_tables) cudaFree(f->d_tc_tables);
     if (f->d_um_tables) cudaFree(f->d_um_tables);
+    if (f->d_uc_tables) cudaFree(f->d_uc_tables);
     for (int i = 0; i < 2; ++i)
         if (f->d_hist[i]) cudaFree(f->d_hist[i]);
     f->d_in.release();
@@ -248,6 +251,18 @@ static int fir_alloc(sdr_fir *f, void *user_stream) {
             SDR_CUDA_TRY(cudaMalloc(&f->d_um_tables, tab.size()));
             SDR_CUDA_TRY(cudaMemcpyAsync(f->d_um_tables, tab.data(), tab.size(), cudaMemcpyHostToDevice, f->stream.s));
             SDR_CUDA_TRY(cudaStreamSynchronize(f->stream.s));
+        }
+    }
+    if (f->fmt == SDR_FMT_C64 && !(f->flags & (SDR_FIR_STRICT_ORDER | SDR_FIR_NO_TENSOR | SDR_FIR_NO_TCGEN05))) {
+        // three bf16 terms per operand (the reference's f32 accuracy) when the tables and planes fit in shared memory
+        // (K <= 384), two terms (< 1e-5 of max|y|) on request or for longer filters
+        const int ns = ((f->flags & SDR_FIR_SPLIT2) || !fir_umma_c64_applies((int)f->K, (int)f->D, f->taps_complex != 0, 3)) ? 2 : 3;
+        std::vector<uint8_t> tab;
+        if (fir_umma_c64_applies((int)f->K, (int)f->D, f->taps_complex != 0, ns) && f->K >= 8 &&
+            fir_umma_c64_build_tables(f->taps.data(), (int)f->K, ns, tab)) {
+            f->uc_ns = ns;
+            SDR_CUDA_TRY(cudaMalloc(&f->d_uc_tables, tab.size()));
+            SDR_CUDA_TRY(cudaMemcpyAsync(f->d_uc_tables, tab.data(), tab.size(), cudaMemcpyHostToDevice, f->stream.s));
         }
     }
     SDR_CUDA_TRY(cudaStreamSynchronize(f->stream.s));
@@ -345,6 +360,10 @@ static int fir_run_dev(sdr_fir *f, const void *in, size_t n_in, size_t in_stride
         rc = fir_umma_launch(a, f->um_R, f->um_PC, f->um_planar, f->d_um_tables, f->um_magic, f->um_sc, f->stream.s);
         if (rc == SDR_OK) f->last_path = 4;
     }
+    if (rc == SDR_ERR_UNSUPPORTED && f->d_uc_tables) {
+        rc = fir_umma_c64_launch(a, f->uc_ns, f->d_uc_tables, f->stream.s);
+        if (rc == SDR_OK) f->last_path = 5;
+    }
     if (rc == SDR_ERR_UNSUPPORTED && f->d_tc_tables) {
         rc = fir_tc_launch(a, f->taps_complex != 0, f->d_tc_tables, f->tc_scale, f->stream.s);
         if (rc == SDR_OK) f->last_path = 3;
@@ -396,10 +415,11 @@ extern "C" int sdr_fir_process(sdr_fir_t *f, const void *in, size_t n_in, size_t
     if (!g.ok) return g.status();
     const size_t es_in = elem_bytes(f->fmt), es_out = (f->fmt == SDR_FMT_F32) ? 4 : 8;
     cudaStream_t st = f->stream.s;
-    // chunks of ~32 MiB of input per channel-set, multiples of 2048*D samples so every chunk but the last keeps the
-    // fast kernel's alignment; H2D(c+1) / kernel(c) / D2H(c-1) overlap
+    // chunks of ~32 MiB of input per channel-set, multiples of 4096*D samples so every chunk but the last keeps the
+    // fast kernels' alignment and tile grid (the c64 tcgen05 kernel's 4096-output tiles then sit at the same stream
+    // positions for any chunking: same bits); H2D(c+1) / kernel(c) / D2H(c-1) overlap
     size_t chunk = std::max<size_t>(1, ((size_t)32 << 20) / (es_in * f->n_ch));
-    chunk = std::max<size_t>(2048 * f->D, chunk / (2048 * f->D) * (2048 * f->D));
+    chunk = std::max<size_t>(4096 * f->D, chunk / (4096 * f->D) * (4096 * f->D));
     if (chunk > n_in) chunk = n_in;
     const size_t out_per_chunk = chunk / f->D + 2;
     const size_t ds_in = round_up(chunk, 8), ds_out = round_up(out_per_chunk, 2);
@@ -1128,8 +1148,9 @@ extern "C" int sdr_channelizer_process_dev(sdr_channelizer_t *c, const void *in,
     if (in_stride < n || out_stride < n) return SDR_ERR_INVALID_ARG;
     DeviceGuard g(c->fir->dev);
     if (!g.ok) return g.status();
-    // slab: keep the c64 intermediate around 32 MiB so it lives in the 126 MB L2
-    size_t slab = std::max<size_t>(2048, (((size_t)32 << 20) / (8 * C)) / 2048 * 2048);
+    // slab: keep the c64 intermediate around 32 MiB so it lives in the 126 MB L2; a multiple of the FIR kernel's
+    // 4096-output tile, so a channel's samples meet the same tile grid however many channels share the handle
+    size_t slab = std::max<size_t>(4096, (((size_t)32 << 20) / (8 * C)) / 4096 * 4096);
     slab = std::min(slab, round_up(n, 8));
     int rc = c->mid.reserve(C * slab * 8);
     if (rc) return rc;

@@ -1173,7 +1173,9 @@ static int fir_umma_poly_launch(const FirArgs &f, const uint8_t *d_tables, const
     a.f = f;
     a.KS = KS;
     a.stages = stages;
-    long long d = (f.first - (f.K - 1)) % 8;
+    // the window start in + 2 (first - (K-1) - delta) must be 16-byte aligned for the 16-byte copies: delta absorbs
+    // both the position of the first needed sample and the alignment of the caller's pointer (any even address)
+    long long d = (f.first - (f.K - 1) + (long long)(((uintptr_t)f.in & 15) >> 1)) % 8;
     if (d < 0) d += 8;
     a.delta = (int)d;
     a.tab = d_tables + (size_t)d * D * KS * 48 * 32;
@@ -1210,14 +1212,16 @@ int fir_umma_launch(const FirArgs &f, int R, int PC, int mode, const uint8_t *d_
     const bool planar = mode == 1;
     if (f.n_out <= 0) return SDR_OK;
     if (mode == 2) {
-        if (f.K > UM_MAX_K || ((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 7) || ((uintptr_t)f.hist & 1) || (f.n_ch > 1 && (f.in_stride & 7)))
+        if (f.K > UM_MAX_K || ((uintptr_t)f.in & 1) || ((uintptr_t)f.out & 7) || ((uintptr_t)f.hist & 1) || (f.n_ch > 1 && (f.in_stride & 7)))
             return SDR_ERR_UNSUPPORTED;
         return fir_umma_poly_launch(f, d_tables, magic, sc, st);
     }
     if (f.K > UM_MAX_K || (f.D == 1 && R != PC) || (f.D != 1 && !planar && R != 32)) return SDR_ERR_UNSUPPORTED;
-    // rows of a multi-channel call must keep the 16-byte alignment of the first one (strides are ignored for one channel)
-    if (((uintptr_t)f.in & 15) || ((uintptr_t)f.out & 15) || ((uintptr_t)f.hist & 1) ||
-        (f.n_ch > 1 && ((f.out_stride & 1) || (f.in_stride & 7))))
+    // rows of a multi-channel call must keep the alignment (mod 16 bytes) of the first one (strides are ignored for one
+    // channel); the input itself may start at any even address: the kernel family gives the SAME bits for every
+    // alignment and blocking, which is what lets a stream be cut across GPUs at arbitrary multiples of D
+    if (((uintptr_t)f.in & 1) || ((uintptr_t)f.out & (planar ? 15 : 7)) || ((uintptr_t)f.hist & 1) ||
+        (f.n_ch > 1 && ((planar && (f.out_stride & 1)) || (f.in_stride & 7))))
         return SDR_ERR_UNSUPPORTED;
     const bool dec = f.D != 1;
     const int KS = planar ? fir_umma_planar_ksteps(f.K, R, PC) : fir_umma_ksteps(f.K, R, PC);
@@ -1230,7 +1234,7 @@ int fir_umma_launch(const FirArgs &f, int R, int PC, int mode, const uint8_t *d_
     a.stages = stages;
     a.f = f;
     a.KS = KS;
-    long long d = (f.first - (f.K - 1)) % 8;
+    long long d = (f.first - (f.K - 1) + (long long)(((uintptr_t)f.in & 15) >> 1)) % 8;  // see fir_umma_poly_launch
     if (d < 0) d += 8;
     a.delta = (int)d;
     a.tab = d_tables + (size_t)d * KS * (planar ? 3 : 6) * PC * 32;

@@ -46,6 +46,12 @@ bool fir_umma_build_tables(const float *taps, int K, bool taps_complex, int R, i
 int fir_umma_launch(const FirArgs &a, int R, int PC, int mode, const uint8_t *d_tables, const int magic[2][3],
                     const float sc[3], cudaStream_t st);
 
+// tcgen05 / TMEM Toeplitz FIR for c64 input, real taps, D == 1 (fir_umma_c64.cu): bf16 split of samples and taps,
+// ns = 3 (six products, f32-grade accuracy) or 2 (three products, < 1e-5 of max|y|)
+bool fir_umma_c64_applies(int K, int D, bool taps_complex, int ns);
+bool fir_umma_c64_build_tables(const float *taps, int K, int ns, std::vector<uint8_t> &out);
+int fir_umma_c64_launch(const FirArgs &a, int ns, const uint8_t *d_tables, cudaStream_t st);
+
 // ---------------------------------------------------------------------------------------
 // FFT (fft.cu)
 // ---------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(_PKG), "lib", "libsdr_b200.so")
 
 FMT_U8IQ, FMT_C64, FMT_F32 = 0, 1, 2
-FIR_STRICT_ORDER, FIR_NO_TENSOR = 1, 2
+FIR_STRICT_ORDER, FIR_NO_TENSOR, FIR_NO_TCGEN05, FIR_PLANAR, FIR_SPLIT2 = 1, 2, 4, 8, 16
 FFT_SHIFT, FFT_NORM, FFT_RFFT = 1, 2, 4
 PLL_FAST_MATH = 1
 BQ_IDENTITY, BQ_LOWPASS, BQ_HIGHPASS, BQ_BANDPASS, BQ_NOTCH, BQ_LR = range(6)
