@@ -120,25 +120,25 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo, uint
 __device__ __forceinline__ uint32_t swz64(uint32_t o) { return o ^ (((o >> 7) & 3u) << 4); }  // SWIZZLE_64B
 __device__ __forceinline__ void prod_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(UC_PROD_WARPS * 32) : "memory"); }
 
-// split 8 f32 values into bf16 terms (round to nearest even) and store one 16-byte chunk per term
+// split 8 f32 values (4 pairs; pair i belongs to word (i + rot) & 3 of the 16-byte chunk) into bf16 terms, round to
+// nearest even, and store one 4-byte word per pair and term
 template <int NS>
-__device__ __forceinline__ void split_store(const float (&v)[8], uint8_t *plane0, int plane_bytes, uint32_t off) {
+__device__ __forceinline__ void split_store(const float (&v)[8], uint8_t *plane0, int plane_bytes, uint32_t off, int rot) {
     float r[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) r[i] = v[i];
 #pragma unroll
     for (int s = 0; s < NS; ++s) {
-        uint32_t w[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const __nv_bfloat162 b = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);  // .x = low half = element 2i
-            w[i] = *reinterpret_cast<const uint32_t *>(&b);
+            const __nv_bfloat162 b = __floats2bfloat162_rn(r[2 * i], r[2 * i + 1]);  // .x = low half = the even element
+            const uint32_t w = *reinterpret_cast<const uint32_t *>(&b);
             if (s + 1 < NS) {
-                r[2 * i] = __fsub_rn(r[2 * i], __uint_as_float(w[i] << 16));
-                r[2 * i + 1] = __fsub_rn(r[2 * i + 1], __uint_as_float(w[i] & 0xFFFF0000u));
+                r[2 * i] = __fsub_rn(r[2 * i], __uint_as_float(w << 16));
+                r[2 * i + 1] = __fsub_rn(r[2 * i + 1], __uint_as_float(w & 0xFFFF0000u));
             }
+            *reinterpret_cast<uint32_t *>(plane0 + (size_t)s * plane_bytes + off + 4u * (uint32_t)((i + rot) & 3)) = w;
         }
-        *reinterpret_cast<uint4 *>(plane0 + (size_t)s * plane_bytes + off) = make_uint4(w[0], w[1], w[2], w[3]);
     }
 }
 
@@ -217,39 +217,51 @@ __global__ void __launch_bounds__(UC_THREADS, 1) fir_umma_c64_kernel(const UcArg
     if (warp < UC_PROD_WARPS) {
         // ================= producers =================
         const int ptid = warp * 32 + lane;
-        auto interior = [&](long long w) {
-            if (w >= nwork) return false;
+        // Elements [e_lo, e_hi) of a tile's window are real input samples at 16-byte aligned addresses: ONE bulk copy.
+        // What is left -- carried history / zeros in front of the stream (fir.rs:15), zeros behind its end, at most one
+        // odd sample at either side -- is a few hundred elements of the first and last tile of a channel: plain stores.
+        auto tma_range = [&](long long w, int &e_lo, int &e_hi) {
+            e_lo = e_hi = 0;
+            if (w >= nwork) return;
             int ch; long long wt;
             split(w, ch, wt);
             const long long s0 = tile_s0(wt);
-            return s0 >= 0 && s0 + NEL <= f.n_in;
+            long long lo = s0 < 0 ? -s0 : 0, hi = f.n_in - s0;
+            if (hi > NEL) hi = NEL;
+            lo = (lo + 1) & ~1LL;
+            hi &= ~1LL;
+            if (hi > lo) { e_lo = (int)lo; e_hi = (int)hi; }
         };
         auto issue_tma = [&](long long w, int slot) {   // one elected thread
+            int e_lo, e_hi;
+            tma_range(w, e_lo, e_hi);
+            if (e_hi <= e_lo) return;
             int ch; long long wt;
             split(w, ch, wt);
-            const float2 *src = (const float2 *)f.in + (long long)ch * f.in_stride + tile_s0(wt);
-            mbar_arrive_expect_tx(raw_bar(slot), (uint32_t)RAWB);
-            tma_bulk_g2s(raw_s + (uint32_t)slot * RAWB, src, (uint32_t)RAWB, raw_bar(slot));
+            const float2 *src = (const float2 *)f.in + (long long)ch * f.in_stride + tile_s0(wt) + e_lo;
+            const uint32_t bytes = 8u * (uint32_t)(e_hi - e_lo);
+            mbar_arrive_expect_tx(raw_bar(slot), bytes);
+            tma_bulk_g2s(raw_s + (uint32_t)slot * RAWB + 8u * (uint32_t)e_lo, src, bytes, raw_bar(slot));
         };
-        if (ptid == 0 && interior(blockIdx.x)) issue_tma(blockIdx.x, 0);
+        if (ptid == 0) issue_tma(blockIdx.x, 0);
         const bool two = a.nraw == 2;
         int stage = 0, slot = 0;
         uint32_t ph = 0, rph[UC_RAW] = {0, 0};
         for (long long w = blockIdx.x; w < nwork; w += wstride) {
             // the next tile's window goes into the other slot (last read one iteration ago, before the closing barrier)
-            if (two && ptid == 0 && interior(w + wstride)) issue_tma(w + wstride, slot ^ 1);
+            if (two && ptid == 0) issue_tma(w + wstride, slot ^ 1);
             uint8_t *rs = raw_g + (size_t)slot * RAWB;
-            if (interior(w)) {
-                mbar_wait(raw_bar(slot), rph[slot]);
-                rph[slot] ^= 1u;
-            } else {
-                // stream start (carried history, then zeros: fir.rs:15) or the ragged end: plain loads
+            int e_lo, e_hi;
+            tma_range(w, e_lo, e_hi);
+            if (e_hi - e_lo < NEL) {
                 int ch; long long wt;
                 split(w, ch, wt);
                 const long long s0 = tile_s0(wt);
                 const float2 *in = (const float2 *)f.in + (long long)ch * f.in_stride;
                 const float2 *hist = (const float2 *)f.hist + (long long)ch * f.hist_stride;
-                for (int e = ptid; e < NEL; e += 32 * UC_PROD_WARPS) {
+                const int n_plain = e_lo + (NEL - e_hi);
+                for (int i = ptid; i < n_plain; i += 32 * UC_PROD_WARPS) {
+                    const int e = i < e_lo ? i : e_hi + (i - e_lo);
                     const long long s = s0 + e;
                     float2 v = make_float2(0.0f, 0.0f);
                     if (s >= 0) { if (s < f.n_in) v = __ldg(in + s); }
@@ -258,26 +270,35 @@ __global__ void __launch_bounds__(UC_THREADS, 1) fir_umma_c64_kernel(const UcArg
                 }
                 prod_bar_sync();
             }
+            if (e_hi > e_lo) {
+                mbar_wait(raw_bar(slot), rph[slot]);
+                rph[slot] ^= 1u;
+            }
             mbar_wait(empty_bar(stage), ph ^ 1u);
             uint8_t *st_g = gen + (size_t)stage * SB;
-            // 8 samples per lane and step: 64 raw bytes -> one 16-byte chunk in each of the 2 NS planes
+            // 8 samples per lane and step: 64 raw bytes -> one 16-byte chunk in each of the 2 NS planes.  A lane's four
+            // 16-byte units sit 64 B from its neighbour's: read in lane order they would hit 2 of the 8 bank groups
+            // (4-way conflicts, ncu: 64 % of the shared wavefronts were replays).  Lane L therefore starts at unit
+            // rot(L) and writes the matching word of each output chunk: loads (8 lanes x 16 B) and stores (32 lanes x 4 B)
+            // are both conflict free, and no register has to be re-ordered.
+            const int rot = ((lane >> 1) + (lane >> 3)) & 3;
 #pragma unroll 2
             for (int c = ptid; c < NEL / 8; c += 32 * UC_PROD_WARPS) {
-                const float4 *src = reinterpret_cast<const float4 *>(rs + 64 * c);
+                const uint8_t *src = rs + 64 * c;
                 float re[8], im[8];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float4 q = src[i];
+                    const float4 q = *reinterpret_cast<const float4 *>(src + 16 * ((i + rot) & 3));
                     re[2 * i] = q.x; im[2 * i] = q.y; re[2 * i + 1] = q.z; im[2 * i + 1] = q.w;
                 }
                 const uint32_t off = swz64(16u * (uint32_t)c);
-                split_store<NS>(re, st_g, PB, off);
-                split_store<NS>(im, st_g + (size_t)NS * PB, PB, off);
+                split_store<NS>(re, st_g, PB, off, rot);
+                split_store<NS>(im, st_g + (size_t)NS * PB, PB, off, rot);
             }
             fence_proxy_async();  // plain stores -> visible to the tensor core's (async proxy) operand reads
             mbar_arrive(full_bar(stage));
             prod_bar_sync();      // every producer is done with this raw slot: it may be refilled
-            if (!two && ptid == 0 && interior(w + wstride)) issue_tma(w + wstride, 0);
+            if (!two && ptid == 0) issue_tma(w + wstride, 0);
             if (++stage == NST) { stage = 0; ph ^= 1u; }
             if (two) slot ^= 1;
         }
