@@ -234,10 +234,16 @@ __host__ __device__ constexpr size_t w1k_smem(int fmt) {
 
 // SHIFT: 0 / 1 = fftshift off / on at compile time (u8 input: the 32 output addresses of a lane become immediates,
 // +2.5 %), 2 = read from the flags at run time (c64 input, where the specialised code measured 7 % slower)
-template <int FMT, int SHIFT>
+// TMA (u8 input): the next transform's 2 KB arrive by ONE cp.async.bulk (UBLKCP) issued by lane 0 and completing on a
+// per-(warp, buffer) mbarrier, instead of four LDGSTS per lane and a wait_group: the same bytes over the same path into
+// shared memory, 128 fewer issued instructions per transform in an issue-bound kernel.  TMA = false keeps the cp.async
+// loader (A/B switch SDR_FFT_NO_TMA=1).
+__device__ __forceinline__ uint32_t w1k_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int FMT, int SHIFT, bool TMA = false>
 __global__ void __launch_bounds__(W1K_WARPS * 32, 2) fft1024_warp_kernel(FftArgs a) {
     constexpr int N = 1024;
     extern __shared__ float4 smem4[];
+    __shared__ __align__(8) uint64_t tma_bar[W1K_WARPS][2];
     float2 *tw_s = reinterpret_cast<float2 *>(smem4);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     float2 *xch = tw_s + 31 * 32 + warp * W1K_XCH;
@@ -257,7 +263,22 @@ __global__ void __launch_bounds__(W1K_WARPS * 32, 2) fft1024_warp_kernel(FftArgs
     const float us = 0.0078125f * fold, uo = -65537.0f * fold;
     const unsigned char *in8 = reinterpret_cast<const unsigned char *>(a.in);
     int buf = 0;
-    if (FMT == SDR_FMT_U8IQ && b < a.batches) {
+    uint32_t tph = 0;  // bit i = parity of buffer i's mbarrier
+    const uint32_t bar_s = w1k_smem_u32(&tma_bar[warp][0]), raw_s = w1k_smem_u32(raw);
+    auto tma_load = [&](long long bb, int bf) {  // lane 0 only
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], 2048;" ::"r"(bar_s + 8u * bf) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 2048, [%2];"
+                     ::"r"(raw_s + 2048u * bf), "l"(in8 + bb * 2048), "r"(bar_s + 8u * bf) : "memory");
+    };
+    if (FMT == SDR_FMT_U8IQ && TMA) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_s + 8u));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            if (b < a.batches) tma_load(b, 0);
+        }
+        __syncwarp();
+    } else if (FMT == SDR_FMT_U8IQ && b < a.batches) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) cp_async16(raw + (i * 32 + lane) * 16, in8 + b * 2048 + (i * 32 + lane) * 16);
         cp_async_commit();
@@ -266,7 +287,15 @@ __global__ void __launch_bounds__(W1K_WARPS * 32, 2) fft1024_warp_kernel(FftArgs
         float2 v[32], w[32];
         if (FMT == SDR_FMT_U8IQ) {
             const long long nb = b + nwarps;
-            if (nb < a.batches) {
+            if (TMA) {
+                // buffer buf ^ 1 was last read one iteration ago, before that iteration's closing __syncwarp
+                if (lane == 0 && nb < a.batches) tma_load(nb, buf ^ 1);
+                uint32_t done = 0;
+                while (!done)
+                    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                                 : "=r"(done) : "r"(bar_s + 8u * buf), "r"((tph >> buf) & 1u) : "memory");
+                tph ^= 1u << buf;
+            } else if (nb < a.batches) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     cp_async16(raw + (buf ^ 1) * 2048 + (i * 32 + lane) * 16, in8 + nb * 2048 + (i * 32 + lane) * 16);
@@ -310,7 +339,10 @@ template <int FMT>
 int launch_w1k(const FftArgs &a, cudaStream_t st) {
     const size_t smem = w1k_smem(FMT);
     const bool shift = (a.flags & SDR_FFT_SHIFT) != 0;
-    auto kern = FMT != SDR_FMT_U8IQ ? fft1024_warp_kernel<FMT, 2> : shift ? fft1024_warp_kernel<FMT, 1> : fft1024_warp_kernel<FMT, 0>;
+    static const bool no_tma = std::getenv("SDR_FFT_NO_TMA") != nullptr;  // A/B switch (tuning)
+    auto kern = FMT != SDR_FMT_U8IQ ? fft1024_warp_kernel<FMT, 2, false>
+                : no_tma ? (shift ? fft1024_warp_kernel<FMT, 1, false> : fft1024_warp_kernel<FMT, 0, false>)
+                         : (shift ? fft1024_warp_kernel<FMT, 1, true> : fft1024_warp_kernel<FMT, 0, true>);
     const int sms = current_sm_count();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
