@@ -301,6 +301,10 @@ int sdr_src_get_channels(SDR_SRC_STATE *);
  * wing + what the last call consumed; a call that stops at `output_frames` hands the input it did
  * not need back through input_frames_used, as libsamplerate's src_process does) */
 long sdr_src_history_frames(SDR_SRC_STATE *);
+/* Sinc converters, long calls (>= 8192 output frames) at an integer step 1/ratio on 2-channel (c64) data run as a
+ * polyphase decimating FIR on the tensor cores: within 1e-5 of max|y| of the converter's f64 specification.
+ * exact != 0 keeps the f64 kernels for every call (equal to the specification up to the final f32 rounding). */
+int sdr_src_set_exact(SDR_SRC_STATE *, int exact);
 const char *sdr_src_strerror(int error);
 const char *sdr_src_get_name(int converter_type);        /* resample.rs:125 */
 const char *sdr_src_get_description(int converter_type); /* resample.rs:133 */

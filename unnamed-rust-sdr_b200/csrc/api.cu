@@ -1219,6 +1219,13 @@ struct sdr_src {
     DevBuf carry;  // ZOH / linear: the frame before in[0]
     DevBuf d_out;
     DevBuf coef;   // sinc: per-phase wing coefficients of the polyphase fast path
+    // tensor-core path (integer step, 2 channels): branch filters' Toeplitz tables, phase planes
+    bool exact = false;            // sdr_src_set_exact: always take the f64 kernels
+    int fast_S = 0, fast_Kb = 0, fast_ns = 0;
+    double fast_ratio = 0.0;
+    uint8_t *d_fast_tab = nullptr; // [S][2 deltas][KS][(32 ns) x 32 B]
+    size_t fast_tab_stride = 0;
+    DevBuf fast_planes;
 };
 
 static bool bad_ratio(double r) { return !(r >= 1.0 / 256.0 && r <= 256.0); }
@@ -1232,7 +1239,8 @@ static void src_free(sdr_src *s) {
     if (!s) return;
     DeviceGuard g(s->dev);
     if (s->d_table) cudaFree(s->d_table);
-    s->v[0].release(); s->v[1].release(); s->carry.release(); s->d_out.release(); s->coef.release();
+    if (s->d_fast_tab) cudaFree(s->d_fast_tab);
+    s->v[0].release(); s->fast_planes.release(); s->v[1].release(); s->carry.release(); s->d_out.release(); s->coef.release();
     s->stream.release();
     delete s;
 }
@@ -1277,6 +1285,11 @@ extern "C" int sdr_src_set_ratio(SDR_SRC_STATE *s, double r) {
     return SDR_OK;
 }
 extern "C" int sdr_src_get_channels(SDR_SRC_STATE *s) { return s ? s->channels : -SDR_ERR_BAD_STATE; }
+extern "C" int sdr_src_set_exact(SDR_SRC_STATE *s, int exact) {
+    if (!s) return SDR_ERR_BAD_STATE;
+    s->exact = exact != 0;
+    return SDR_OK;
+}
 extern "C" long sdr_src_history_frames(SDR_SRC_STATE *s) {
     if (!s) return -SDR_ERR_BAD_STATE;
     return s->type >= SDR_SRC_ZERO_ORDER_HOLD ? (s->fresh ? 0 : 1) : (long)s->kept;
@@ -1319,6 +1332,7 @@ extern "C" SDR_SRC_STATE *sdr_src_clone(SDR_SRC_STATE *o, int *error) {
     if (!s) return nullptr;
     s->ratio = o->ratio; s->fresh = o->fresh; s->pos = o->pos; s->spos = o->spos; s->kept = o->kept;
     s->total_in = o->total_in; s->origin_abs = o->origin_abs; s->ended = o->ended; s->cur = 0;
+    s->exact = o->exact;
     DeviceGuard g(s->dev);
     const bool zl = (o->type >= SDR_SRC_ZERO_ORDER_HOLD);
     const size_t bytes = (size_t)(zl ? 1 : o->kept) * o->channels * sizeof(float);
@@ -1341,6 +1355,63 @@ static long long count_outputs(long long cap, F &&ok) {
         if (ok(mid)) lo = mid + 1; else hi = mid;
     }
     return lo;
+}
+
+// Long calls at an integer step (ratio 1/S: the reference's 240 k -> 48 k and 144 k -> 48 k conversions) on a c64 stream:
+// the sinc converter IS a polyphase decimating FIR with fixed taps, and runs as S branch filters on the tcgen05 Toeplitz
+// kernel (fir_umma_c64.cu) instead of 2 wc f64 multiply-adds per output on the 64-lane f64 pipe.  f32 accumulation of
+// bf16-split operands: within 1e-5 of max|y| of the f64 specification (north star tolerance for "resample"; measured
+// ~1e-6); sdr_src_set_exact(state, 1) keeps the f64 kernels (equal to the specification up to the final f32 rounding).
+constexpr long long SRC_FAST_MIN_OUT = 8192;
+static int src_fast_run(sdr_src *s, const SrcLaunch &L, cudaStream_t st) {
+    if (L.channels != 2 || L.type > SDR_SRC_SINC_FASTEST || L.origin != 0) return SDR_ERR_UNSUPPORTED;
+    const double step = L.step;
+    const long long S = (long long)step;
+    if ((double)S != step || S < 1 || S > 64) return SDR_ERR_UNSUPPORTED;
+    const long long P = (long long)L.pos;
+    if ((double)P != L.pos || P < 0) return SDR_ERR_UNSUPPORTED;
+    if (((uintptr_t)L.out & 15) || ((uintptr_t)L.v & 7)) return SDR_ERR_UNSUPPORTED;
+    const int Kb = src_fast_branch_len(L.wc, (int)S);
+    const int ns = fir_umma_c64_applies(Kb, 1, false, 3) ? 3 : 2;
+    if (!fir_umma_c64_applies(Kb, 1, false, ns)) return SDR_ERR_UNSUPPORTED;
+    const double ratio = 1.0 / step;
+    if (!s->d_fast_tab || s->fast_S != (int)S || s->fast_Kb != Kb || s->fast_ns != ns || s->fast_ratio != ratio) {
+        // (re)build the branch filters' Toeplitz tables: once per (converter, ratio), reused by every later call
+        std::vector<float> br;
+        src_fast_taps(s->type, ratio, (int)S, br);
+        std::vector<uint8_t> all, one;
+        for (long long b = 0; b < S; ++b) {
+            if (!fir_umma_c64_build_tables(br.data() + (size_t)b * Kb, Kb, ns, one)) return SDR_ERR_UNSUPPORTED;
+            all.insert(all.end(), one.begin(), one.end());
+        }
+        if (s->d_fast_tab) { cudaStreamSynchronize(st); cudaFree(s->d_fast_tab); s->d_fast_tab = nullptr; }
+        SDR_CUDA_TRY(cudaMalloc(&s->d_fast_tab, all.size()));
+        SDR_CUDA_TRY(cudaMemcpyAsync(s->d_fast_tab, all.data(), all.size(), cudaMemcpyHostToDevice, st));
+        SDR_CUDA_TRY(cudaStreamSynchronize(st));  // `all` is pageable host memory
+        s->fast_tab_stride = one.size();
+        s->fast_S = (int)S; s->fast_Kb = Kb; s->fast_ns = ns; s->fast_ratio = ratio;
+    }
+    const int hl = (Kb + 2 + 1) & ~1;                       // history region in front of each plane (even: planes stay 16-byte aligned)
+    const long long pitch = ((long long)hl + L.n_out + 7) & ~7LL;
+    int rc = s->fast_planes.reserve((size_t)S * pitch * sizeof(float2));
+    if (rc) return rc;
+    float *planes = (float *)s->fast_planes.p;
+    rc = src_fast_gather(L.v, L.have, P, L.wc + 1, (int)S, planes, pitch, hl, L.n_out, st);
+    if (rc) return rc;
+    for (long long b = 0; b < S; ++b) {
+        FirArgs a;
+        a.in = planes + 2 * (b * pitch + hl);
+        a.hist = planes + 2 * (b * pitch);
+        a.out = L.out;
+        a.taps = nullptr;
+        a.n_in = L.n_out; a.in_stride = L.n_out; a.out_stride = L.n_out; a.hist_stride = hl; a.n_out = L.n_out;
+        a.first = 0;
+        a.K = Kb; a.Kp = Kb; a.HL = hl; a.D = 1; a.n_ch = 1;
+        a.accumulate = b > 0;
+        rc = fir_umma_c64_launch(a, ns, s->d_fast_tab + (size_t)b * s->fast_tab_stride, st);
+        if (rc) return rc;   // (UNSUPPORTED cannot happen after branch 0 went through: same geometry)
+    }
+    return SDR_OK;
 }
 
 static int src_process_impl(sdr_src *s, SDR_SRC_DATA *d, bool dev_ptrs) {
@@ -1462,9 +1533,13 @@ static int src_process_impl(sdr_src *s, SDR_SRC_DATA *d, bool dev_ptrs) {
         dout = (float *)s->d_out.p;
     }
     L.out = dout;
-    if ((size_t)(wc + 6) * 64 * sizeof(double) <= ((size_t)64 << 20) && s->coef.reserve((size_t)(wc + 6) * 64 * sizeof(double)) == SDR_OK)
-        L.coef = (double *)s->coef.p;
-    rc = src_launch(L, st);
+    rc = SDR_ERR_UNSUPPORTED;
+    if (!s->exact && m >= SRC_FAST_MIN_OUT) rc = src_fast_run(s, L, st);
+    if (rc == SDR_ERR_UNSUPPORTED) {
+        if ((size_t)(wc + 6) * 64 * sizeof(double) <= ((size_t)64 << 20) && s->coef.reserve((size_t)(wc + 6) * 64 * sizeof(double)) == SDR_OK)
+            L.coef = (double *)s->coef.p;
+        rc = src_launch(L, st);
+    }
     if (rc) return rc;
     if (!dev_ptrs && m > 0) SDR_CUDA_TRY(cudaMemcpyAsync(d->data_out, dout, (size_t)m * fb, cudaMemcpyDeviceToHost, st));
     d->output_frames_gen = (long)m;

@@ -394,10 +394,16 @@ __global__ void __launch_bounds__(UC_THREADS, 1) fir_umma_c64_kernel(const UcArg
                                     for (int s = NS - 2; s >= 0; --s) acc += __uint_as_float(e[part][s][i0 + q]);
                                     y[part][q] = acc;
                                 }
-                            if (full || (long long)(off + 1) < left)
-                                *reinterpret_cast<float4 *>(out + m_base + off) = make_float4(y[0][0], y[1][0], y[0][1], y[1][1]);
-                            else
-                                out[m_base + off] = make_float2(y[0][0], y[1][0]);
+                            if (full || (long long)(off + 1) < left) {
+                                float4 *dst = reinterpret_cast<float4 *>(out + m_base + off);
+                                float4 r = make_float4(y[0][0], y[1][0], y[0][1], y[1][1]);
+                                if (f.accumulate) { const float4 o = *dst; r.x += o.x; r.y += o.y; r.z += o.z; r.w += o.w; }
+                                *dst = r;
+                            } else {
+                                float2 r = make_float2(y[0][0], y[1][0]);
+                                if (f.accumulate) { const float2 o = out[m_base + off]; r.x += o.x; r.y += o.y; }
+                                out[m_base + off] = r;
+                            }
                         }
                     }
             }

@@ -15,6 +15,7 @@ struct FirArgs {
     long long n_in, in_stride, out_stride, hist_stride, n_out;
     long long first;   // index (in new-input coordinates) of the first kept output
     int K, Kp, HL, D, n_ch;
+    int accumulate = 0;  // c64 tcgen05 kernel only: out += result (the polyphase branches of the rational resampler)
 };
 // fmt: sdr_format_t.  Picks the register-blocked kernel when D == 1 and alignment allows,
 // the generic one otherwise.  *path: 1 = direct (FMA), 2 = strict order.
@@ -137,6 +138,14 @@ struct SrcLaunch {
     double *coef = nullptr;
 };
 int src_launch(const SrcLaunch &s, cudaStream_t st);
+// Rational-ratio sinc conversion as a polyphase decimating FIR on the tensor cores (integer step S = 1/ratio, integer
+// positions, 2 channels = one c64 stream): y[m] = sum_s FIR_{g_s}(x_s)[m], x_s[u] = v[S u + P + W - s], g_s[t] = g[S t + s],
+// g[k] = rho * coef(|W - k|), W = wc + 1.  src_fast_taps fills the S branch filters (each Kb taps, zero padded);
+// src_fast_gather writes the S phase planes (hl zero / history elements, then n_out elements each, pitch plane_pitch).
+int src_fast_branch_len(long long wc, int S);
+void src_fast_taps(int type, double ratio, int S, std::vector<float> &branches);
+int src_fast_gather(const float *v, long long have, long long P, long long W, int S, float *planes, long long plane_pitch,
+                    int hl, long long n_out, cudaStream_t st);
 // the windowed-sinc half table of converter `type` (0..2), computed once on the host in f64
 size_t src_sinc_table_host(int type, const float **table, int *increment);
 double src_sinc_wing(int type, double ratio, double *rq, double *rho, long long *wc);

@@ -524,6 +524,55 @@ double src_sinc_wing(int type, double ratio, double *rq, double *rho, long long 
     return wing;
 }
 
+// ---- tensor-core path for integer steps (see kernels.h) -----------------------------------------------------------
+// taps of the equivalent FIR: g[k] = rho * coef(|W - k|), k = 0 .. 2W, coef = the spec's linear interpolation in the
+// half table evaluated in f64 (the same expression as src_sinc_coef_kernel / the per-tap kernel), rounded to f32 once.
+int src_fast_branch_len(long long wc, int S) { return (int)((2 * (wc + 1) + 1 + S - 1) / S); }
+
+void src_fast_taps(int type, double ratio, int S, std::vector<float> &branches) {
+    double rq, rho;
+    long long wc;
+    src_sinc_wing(type, ratio, &rq, &rho, &wc);
+    const float *tab = nullptr;
+    int inc = 0;
+    const long long half_len = (long long)src_sinc_table_host(type, &tab, &inc);
+    const long long W = wc + 1, Kt = 2 * W + 1;
+    const int Kb = src_fast_branch_len(wc, S);
+    branches.assign((size_t)S * Kb, 0.0f);
+    for (long long k = 0; k < Kt; ++k) {
+        const long long d = k <= W ? W - k : k - W;
+        const double fi = (double)d * rq;
+        const long long idx = (long long)fi;
+        double co = 0.0;
+        if (idx < half_len) {
+            const double fr = fi - (double)idx;
+            co = (double)tab[idx] + fr * ((double)tab[idx + 1] - (double)tab[idx]);
+        }
+        branches[(size_t)(k % S) * Kb + (size_t)(k / S)] = (float)(rho * co);
+    }
+}
+
+// planes[s][hl + u] = v[S u + P + W - s] (frame = one c64), zero outside [0, have); u = -hl .. n_out - 1
+__global__ void src_fast_gather_kernel(const float2 *__restrict__ v, long long have, long long base, int S,
+                                       float2 *__restrict__ planes, long long pitch, int hl, long long n_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int s = blockIdx.y;
+    if (i >= n_out + hl) return;
+    const long long j = (long long)S * (i - hl) + base - s;
+    float2 x = make_float2(0.0f, 0.0f);
+    if (j >= 0 && j < have) x = __ldg(v + j);
+    planes[(long long)s * pitch + i] = x;
+}
+
+int src_fast_gather(const float *v, long long have, long long P, long long W, int S, float *planes, long long plane_pitch,
+                    int hl, long long n_out, cudaStream_t st) {
+    const long long per = n_out + hl;
+    dim3 grid((unsigned)((per + 255) / 256), (unsigned)S);
+    src_fast_gather_kernel<<<grid, 256, 0, st>>>((const float2 *)v, have, P + W, S, (float2 *)planes, plane_pitch, hl, n_out);
+    count_launch();
+    return launch_status();
+}
+
 // the polyphase path applies when every position of the call is exact in f64 (see above); fills PolyArgs
 static bool poly_plan(const SrcLaunch &s, PolyArgs &a) {
     static const bool disabled = std::getenv("SDR_SRC_NO_POLY") != nullptr;  // A/B switch for the parity test

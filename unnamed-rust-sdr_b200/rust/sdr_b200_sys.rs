@@ -188,6 +188,7 @@ extern "C" {
     pub fn sdr_src_set_ratio(s: *mut SDR_SRC_STATE, new_ratio: c_double) -> c_int;
     pub fn sdr_src_get_channels(s: *mut SDR_SRC_STATE) -> c_int;
     pub fn sdr_src_history_frames(s: *mut SDR_SRC_STATE) -> c_long;
+    pub fn sdr_src_set_exact(s: *mut SDR_SRC_STATE, exact: c_int) -> c_int;
     pub fn sdr_src_strerror(error: c_int) -> *const c_char;
     pub fn sdr_src_get_name(converter_type: c_int) -> *const c_char;
     pub fn sdr_src_get_description(converter_type: c_int) -> *const c_char;

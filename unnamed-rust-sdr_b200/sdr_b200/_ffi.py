@@ -129,6 +129,7 @@ PROTOTYPES = {
     "sdr_src_set_ratio": (i32, [vp, C.c_double]),
     "sdr_src_get_channels": (i32, [vp]),
     "sdr_src_history_frames": (C.c_long, [vp]),
+    "sdr_src_set_exact": (i32, [vp, i32]),
     "sdr_src_strerror": (C.c_char_p, [i32]),
     "sdr_src_get_name": (C.c_char_p, [i32]),
     "sdr_src_get_description": (C.c_char_p, [i32]),

@@ -612,6 +612,13 @@ class SampleRate:
     def history_frames(self):
         return lib().sdr_src_history_frames(self.h)
 
+    def set_exact(self, exact=True):
+        """True: always the f64 kernels (the converter's specification up to the final f32 rounding); False (default):
+        long integer-step calls on c64 data may take the tensor-core polyphase path (within 1e-5 of max|y|)"""
+        rc = lib().sdr_src_set_exact(self.h, 1 if exact else 0)
+        if rc:
+            raise ResampleError(rc)
+
     def close(self):
         if getattr(self, "h", None):
             lib().sdr_src_delete(self.h)
