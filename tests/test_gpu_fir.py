@@ -109,6 +109,52 @@ def test_tcgen05_path_is_alignment_invariant(sdr, K, D, tc):
                 assert np.array_equal(y.view(np.uint32), ref.view(np.uint32)), (off, ooff)
 
 
+def test_tcgen05_tma_staging_gives_the_same_bits(sdr):
+    """fir_umma_kernel can stage its sliding window by TMA tensor copies (SDR_UMMA_TMA=1; off by default because it
+    measured 4-5 % slower than cp.async on C1, see fir_umma.cu).  Both loaders must put the same bytes in the same
+    places: every output bit equal, for the three row widths, decimation, several channels, odd pointer alignment
+    and stream lengths that end inside a window row."""
+    import subprocess
+    import sys
+    import tempfile
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import gen, sdr_b200 as sdr, torch
+outs = []
+dev = torch.device("cuda", 0)
+for K, D, tc, n_ch, n in ((64, 1, False, 1, 70000), (64, 1, True, 1, 2 * 4096 + 4112), (255, 1, False, 3, 30000), (1, 3, False, 1, 9006),
+                          (64, 3, True, 1, 41000), (255, 2, False, 2, 50000), (17, 1, False, 1, 12345), (300, 4, False, 1, 66000)):
+    rng = np.random.default_rng(K + D)
+    taps = (rng.standard_normal(K) / np.sqrt(K)).astype(np.float32)
+    if tc:
+        taps = (taps + 1j * rng.standard_normal(K) / np.sqrt(K)).astype(np.complex64)
+    iq = gen.random_u8(2 * n_ch * n, K * 7 + D).reshape(n_ch, 2 * n)
+    f = sdr.Fir(taps, "u8iq", decimation=D, n_channels=n_ch)
+    a = f.process(np.ascontiguousarray(iq[:, :2 * 777]))
+    b = f.process(np.ascontiguousarray(iq[:, 2 * 777:]))
+    assert f.last_path == 4, (K, D, f.last_path)
+    outs += [a.ravel().view(np.float32), b.ravel().view(np.float32)]
+    if n_ch == 1:   # device pointer at an odd alignment
+        buf = torch.zeros(2 * n + 64, dtype=torch.uint8, device=dev)
+        buf[6:6 + 2 * n] = torch.from_numpy(iq[0]).to(dev)
+        g = sdr.Fir(taps, "u8iq", decimation=D)
+        o = torch.zeros(g.output_count(n) + 1, dtype=torch.complex64, device=dev)
+        got = g.process_dev(buf[6:6 + 2 * n], n, o, o.numel())
+        torch.cuda.synchronize()
+        outs.append(o[:got].cpu().numpy().view(np.float32))
+np.save(sys.argv[1], np.concatenate(outs))
+""" % (os.path.join(os.path.dirname(__file__), "..", "unnamed-rust-sdr_b200"), os.path.dirname(__file__))
+    res = []
+    for extra in ({}, {"SDR_UMMA_TMA": "1"}, {"SDR_UMMA_TMA": "1", "SDR_UMMA_P": "16"}, {"SDR_UMMA_P": "16"}):
+        with tempfile.NamedTemporaryFile(suffix=".npy") as f:
+            subprocess.check_call([sys.executable, "-c", code, f.name], env=dict(os.environ, **extra))
+            res.append(np.load(f.name))
+    assert res[0].size > 300000
+    assert np.array_equal(res[0].view(np.uint32), res[1].view(np.uint32))
+    assert np.array_equal(res[2].view(np.uint32), res[3].view(np.uint32))
+
+
 SPLIT2 = 16  # SDR_FIR_SPLIT2
 
 

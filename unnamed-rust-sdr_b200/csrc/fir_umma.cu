@@ -45,6 +45,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cuda.h>  // CUtensorMap and the cuTensorMapEncodeTiled prototype only: the entry point is resolved at run time
+
 #include "kernels.h"
 
 namespace sdr {
@@ -71,6 +73,11 @@ struct UmArgs {
     unsigned dmagic;     // floor(2^32 / D) + 1: n / D == umulhi(n, dmagic) for n < 2^17, D <= 4096
     int magic[2][3];     // [part]: {-(256 C1 + C0), unused, 0x4B400000 - C2}, C_d = 128 * sum of that column's digit-d taps
     float sc[3];         // 2^-(S+7) * {1, 256, 65536}
+    // TMA (fir_umma_kernel): interior tiles are staged by tma_nbox tensor copies of tma_rows window rows each
+    int use_tma = 0, tma_rows = 0, tma_nbox = 0;
+    int tma_shift = 0;   // bytes the tensor map's base sits below the caller's `in` (16-byte alignment of the map)
+    int tma_need = 0;    // window rows a tile really reads (the boxes are rounded up to multiples of 8 rows)
+    long long tma_rows_total = 0;  // rows of the map: a tile whose needed rows reach beyond it is staged by cp.async
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------------
@@ -92,6 +99,18 @@ __device__ __forceinline__ void cp_async16_s(uint32_t dst, const void *src) {
 }
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// TMA tensor copies global -> shared (SASS: UTMALDG), completion in bytes on an mbarrier
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, int c3, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -155,7 +174,7 @@ __device__ __forceinline__ void split_work(long long w, int ntiles, int n_ch, in
 }
 
 template <int R, int PC, bool DEC>
-__global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a) {
+__global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a, const __grid_constant__ CUtensorMap tmap) {
     constexpr int P = R;                     // (name kept from the D == 1 derivation: outputs per row when PC == R)
     constexpr int MB = 32 / PC;              // 128-row blocks per tile
     constexpr int N = 6 * PC;                // MMA N: 3 digits x PC candidates x (I, Q)
@@ -217,7 +236,29 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_kernel(const UmArgs a)
             mbar_wait(empty_bar(stage), ph ^ 1u);
             const uint32_t sbase = stage0 + (uint32_t)stage * SB;
             bool slow = false;
-            if (w0 >= 0 && w0 + 8LL * nchunks <= f.n_in) {
+            if (w0 >= 0 && w0 + 8LL * nchunks <= f.n_in && a.use_tma &&
+                (2 * w0 + a.tma_shift) / ROWB + a.tma_need <= a.tma_rows_total) {
+                // interior tile, TMA: the sliding window with its tap-length halo is ONE tensor copy (two when it has
+                // more than 256 rows) issued by one thread.  The map views the byte stream as rows of ROWB bytes that
+                // may start at any 16-byte offset ({ROWB, ROWB/16 sub-offsets, rows[, channel]}), the box is
+                // {ROWB, 1, rows}, and the map's swizzle mode is the A descriptor's: the bytes land exactly where the
+                // cp.async loop below puts them.  Rows past the end of the stream are zero-filled by the hardware
+                // (they feed only outputs that are never stored).
+                if (ptid == 0) {
+                    const long long b0 = 2 * w0 + a.tma_shift;  // byte offset from the map's base: a multiple of 16
+                    const int c1 = (int)((b0 / 16) % (ROWB / 16)), c2 = (int)(b0 / ROWB);
+                    mbar_arrive_expect_tx(full_bar(stage), (uint32_t)(a.tma_nbox * a.tma_rows * ROWB));
+                    for (int i = 0; i < a.tma_nbox; ++i) {
+                        const uint32_t dst = sbase + (uint32_t)(i * a.tma_rows * ROWB);
+                        if (f.n_ch == 1) tma_load_3d(dst, &tmap, 0, c1, c2 + i * a.tma_rows, full_bar(stage));
+                        else tma_load_4d(dst, &tmap, 0, c1, c2 + i * a.tma_rows, ch, full_bar(stage));
+                    }
+                } else {
+                    mbar_arrive(full_bar(stage));
+                }
+                if (++stage == NST) { stage = 0; ph ^= 1u; }
+                continue;
+            } else if (w0 >= 0 && w0 + 8LL * nchunks <= f.n_in) {
                 // interior tile (all but the first / last of a block): nothing but address arithmetic and LDGSTS
                 const unsigned char *src = in + 2 * w0;
 #pragma unroll 4
@@ -1208,6 +1249,66 @@ static int fir_umma_poly_launch(const FirArgs &f, const uint8_t *d_tables, const
     return SDR_ERR_UNSUPPORTED;
 }
 
+// cuTensorMapEncodeTiled, resolved through the runtime (no link-time dependency on libcuda); null = not available
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// Tensor map over the raw byte stream for fir_umma_kernel's stages: {ROWB bytes, ROWB/16 sub-offsets (stride 16 B),
+// rows (stride ROWB)[, channels (stride 2 in_stride)]}, box {ROWB, 1, rows, 1}, swizzle = the A descriptor's.  Returns
+// false when TMA cannot serve this call (the kernel then stages with cp.async, same bytes in the same places).
+static bool um_make_tensor_map(const FirArgs &f, int R, int nchunks, int stage_bytes, UmArgs &a, CUtensorMap *tm) {
+    // MEASURED (round 2, A/B on one box, profiles/r02_ab_tma.txt): with 64-byte box rows at 16-byte sub-offsets the tensor
+    // copy is 4-5 % SLOWER than the three LDGSTS producer warps on the HBM-bound 64-tap configs (C1 457-461 vs 482-487,
+    // complex taps 447-455 vs 467-473 Gsamples/s) and equal on the tensor-bound 255-tap one (311 vs 312).  The stage layout
+    // forces small rows (the window rows' pitch IS the swizzle width), and a 1-D bulk copy cannot swizzle.  So this
+    // kernel keeps cp.async by default and takes the TMA path with SDR_UMMA_TMA=1 (same bytes in the same places:
+    // test_tcgen05_tma_staging_gives_the_same_bits); the c64 FIR and the 1024-point FFT, whose stages are plain linear
+    // copies, use TMA bulk copies unconditionally.
+    static const bool on = std::getenv("SDR_UMMA_TMA") != nullptr;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!on || !enc) return false;
+    const int W = 2 * R;
+    const uintptr_t addr = (uintptr_t)f.in;
+    const int shift = (int)(addr & 15);
+    const long long nbytes = 2 * f.n_in + shift;
+    const long long rows_total = (nbytes - (W - 16)) / W;
+    if (rows_total < 1) return false;
+    const int need_rows = (16 * nchunks + W - 1) / W;
+    const int nbox = (need_rows + 255) / 256;
+    int rows = ((need_rows + nbox - 1) / nbox + 7) & ~7;  // multiples of 8 rows keep the swizzle period between boxes
+    if (rows > 256 || (long long)nbox * rows * W > stage_bytes) return false;
+    const bool multi = f.n_ch > 1;
+    if (multi && ((2 * f.in_stride) % 16 != 0 || 2 * f.in_stride >= (1LL << 40))) return false;
+    cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)(W / 16), (cuuint64_t)rows_total, (cuuint64_t)f.n_ch};
+    cuuint64_t strides[3] = {16, (cuuint64_t)W, (cuuint64_t)(2 * f.in_stride)};  // bytes, dims 1..3
+    cuuint32_t box[4] = {(cuuint32_t)W, 1, (cuuint32_t)rows, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUtensorMapSwizzle sw = R == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : R == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    const CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, multi ? 4 : 3, (void *)(addr - shift), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    a.use_tma = 1;
+    a.tma_rows = rows;
+    a.tma_nbox = nbox;
+    a.tma_shift = shift;
+    a.tma_need = need_rows + 1;  // + 1: a window that starts at a 16-byte sub-offset spills into one more row
+    a.tma_rows_total = rows_total;
+    return true;
+}
+
 int fir_umma_launch(const FirArgs &f, int R, int PC, int mode, const uint8_t *d_tables, const int magic[2][3], const float sc[3], cudaStream_t st) {
     const bool planar = mode == 1;
     if (f.n_out <= 0) return SDR_OK;
@@ -1256,6 +1357,21 @@ int fir_umma_launch(const FirArgs &f, int R, int PC, int mode, const uint8_t *d_
         count_launch();
         return launch_status();
     };
+    // interleaved-bytes kernel: stages through TMA when a tensor map can be built for this call
+    CUtensorMap tm;
+    std::memset(&tm, 0, sizeof(tm));
+    if (!planar) {
+        const int MB = 32 / PC, ROWB = 2 * R;
+        const int nchunks = (ROWB * (128 * MB - 1) + 32 * KS + 15) / 16;
+        um_make_tensor_map(f, R, nchunks, a.stage_bytes, a, &tm);
+    }
+    auto go_tm = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return cuda_status(e);
+        kern<<<grid, UM_THREADS, smem, st>>>(a, tm);
+        count_launch();
+        return launch_status();
+    };
     if (planar) {
         if (!dec && R == 16) return go(fir_umma_planar_kernel<16, 16, false>);
         if (!dec && R == 32) return go(fir_umma_planar_kernel<32, 32, false>);
@@ -1267,15 +1383,15 @@ int fir_umma_launch(const FirArgs &f, int R, int PC, int mode, const uint8_t *d_
     }
     if (!dec) {
         switch (R) {
-            case 8: return go(fir_umma_kernel<8, 8, false>);
-            case 16: return go(fir_umma_kernel<16, 16, false>);
-            case 32: return go(fir_umma_kernel<32, 32, false>);
+            case 8: return go_tm(fir_umma_kernel<8, 8, false>);
+            case 16: return go_tm(fir_umma_kernel<16, 16, false>);
+            case 32: return go_tm(fir_umma_kernel<32, 32, false>);
         }
     } else if (R == 32) {
         switch (PC) {
-            case 8: return go(fir_umma_kernel<32, 8, true>);
-            case 16: return go(fir_umma_kernel<32, 16, true>);
-            case 32: return go(fir_umma_kernel<32, 32, true>);
+            case 8: return go_tm(fir_umma_kernel<32, 8, true>);
+            case 16: return go_tm(fir_umma_kernel<32, 16, true>);
+            case 32: return go_tm(fir_umma_kernel<32, 32, true>);
         }
     }
     return SDR_ERR_UNSUPPORTED;
