@@ -421,7 +421,10 @@ __device__ __forceinline__ void reg2_middle(float2 *sx, const float2 *tab, int t
     group_sync<TC>(group);
 }
 
-template <int LOGN, int FMT>
+// REGPF (n = 8192, c64): the next transform's pass-0 inputs are prefetched into REGISTERS (16 LDG.64 per thread, issued
+// behind pass 0, consumed one transform later) instead of a cp.async raw copy in shared memory: the raw copy cost 128 KB
+// of the 512 KB of shared-memory traffic per transform in a kernel whose phases are serialised by CTA-wide barriers.
+template <int LOGN, int FMT, bool REGPF = false>
 __global__ void __launch_bounds__(Reg2Plan<LOGN>::THREADS, (Reg2Plan<LOGN>::THREADS <= 256) ? 2 : 1)
 fft_reg2_kernel(FftArgs a) {
     using PL = Reg2Plan<LOGN>;
@@ -457,8 +460,13 @@ fft_reg2_kernel(FftArgs a) {
 
     const bool shift = (a.flags & SDR_FFT_SHIFT) != 0 && !(a.flags & SDR_FFT_RFFT);
     const int out_len = (a.flags & SDR_FFT_RFFT) ? N - N / 2 : N;
-    constexpr bool PF = PL::PREFETCH;
+    constexpr bool PF = PL::PREFETCH && !REGPF;
     constexpr int ES = FmtBytes<FMT>::v;
+    float2 nx[REGPF ? 16 : 1];
+    if (REGPF && (long long)blockIdx.x * SEQ + group < a.batches) {
+#pragma unroll
+        for (int e = 0; e < 16; ++e) nx[REGPF ? e : 0] = load_elem<FMT>(a.in, ((long long)blockIdx.x * SEQ + group) * N + t + e * TC);
+    }
     unsigned char *raw = reinterpret_cast<unsigned char *>(smem4) + PL::raw_offset();
     auto issue_raw = [&](long long b) {
         const unsigned char *src = reinterpret_cast<const unsigned char *>(a.in) + b * N * ES;
@@ -482,6 +490,14 @@ fft_reg2_kernel(FftArgs a) {
             for (int e = 0; e < 16; ++e) v[e] = raw_elem<FMT>(raw, t + e * TC);
             __syncthreads();  // the raw buffer is free: fetch the next transform behind this one's arithmetic
             if (b0 + gridDim.x < a.batches) issue_raw(b0 + gridDim.x);
+        } else if (REGPF) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = nx[REGPF ? e : 0];
+            const long long nb = b + (long long)gridDim.x * SEQ;
+            if (nb < a.batches) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) nx[REGPF ? e : 0] = load_elem<FMT>(a.in, nb * N + t + e * TC);
+            }
         } else {
 #pragma unroll
             for (int e = 0; e < 16; ++e) v[e] = live ? load_elem<FMT>(a.in, b * N + t + e * TC) : make_float2(0.f, 0.f);
@@ -533,9 +549,13 @@ int launch_cta(const FftArgs &a, cudaStream_t st);
 template <int LOGN, int FMT>
 int launch_reg2(const FftArgs &a, cudaStream_t st) {
     using PL = Reg2Plan<LOGN>;
-    const size_t smem = PL::smem_bytes(FmtBytes<FMT>::v);
-    if (PL::PREFETCH && (((uintptr_t)a.in) & 15)) return launch_cta<LOGN, FMT>(a, st);  // cp.async needs 16-byte rows
-    auto kern = fft_reg2_kernel<LOGN, FMT>;
+    static const int mode8k = std::getenv("SDR_FFT8K") ? std::atoi(std::getenv("SDR_FFT8K")) : 1;  // A/B switch: 0 = cp.async raw copy
+    constexpr bool CAN_REGPF = PL::PREFETCH && FMT == SDR_FMT_C64;
+    const bool regpf = CAN_REGPF && mode8k == 1;
+    const size_t smem = regpf ? PL::raw_offset() : PL::smem_bytes(FmtBytes<FMT>::v);
+    if (!regpf && PL::PREFETCH && (((uintptr_t)a.in) & 15)) return launch_cta<LOGN, FMT>(a, st);  // cp.async needs 16-byte rows
+    void (*kern)(FftArgs) = fft_reg2_kernel<LOGN, FMT, false>;
+    if constexpr (CAN_REGPF) { if (regpf) kern = fft_reg2_kernel<LOGN, FMT, true>; }
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return cuda_status(e);
     const int sms = current_sm_count();
