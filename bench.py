@@ -720,6 +720,24 @@ def main():
         raise SystemExit("bench.py: no CUDA device (libsdr_b200 has no CPU fallback)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+
+    # CPU leg first, on rank 0, BEFORE the process group exists: the other ranks then wait in the rendezvous (a blocking
+    # socket read), not in a spinning NCCL barrier that would take host cores away from the baseline
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        import oracle_lib as O
+        threads = O.hardware_threads()
+        fn, units = cpu_leg(args.workload)
+        fn(units // 16, threads)
+        secs = fn(units, threads)
+        u1 = max(units // max(threads, 1), 1 << 16)
+        secs1 = fn(u1, 1)
+        cpu = {"value": units / secs / 1e9, "unit": "Gsamples/s", "cores": threads, "kind": "port",
+               "sample": "%d samples of the same workload" % units, "single_thread_value": u1 / secs1 / 1e9}
+        if args.workload in ("c2", "default", "fft1024_u8"):
+            cpu["optimised_cpu"] = numpy_fft_line(threads)
+        _CPU_INPUT.clear()
+
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -781,20 +799,6 @@ def main():
             except Exception as e:  # one failing secondary config must not take the headline line with it
                 configs.append({"workload": config_dict(name)["workload"], "error": repr(e)[:300]})
                 torch.cuda.empty_cache()
-
-    cpu = None
-    if rank == 0 and not args.no_cpu:
-        import oracle_lib as O
-        threads = O.hardware_threads()
-        fn, units = cpu_leg(args.workload)
-        fn(units // 16, threads)
-        secs = fn(units, threads)
-        u1 = max(units // max(threads, 1), 1 << 16)
-        secs1 = fn(u1, 1)
-        cpu = {"value": units / secs / 1e9, "unit": "Gsamples/s", "cores": threads, "kind": "port",
-               "sample": "%d samples of the same workload" % units, "single_thread_value": u1 / secs1 / 1e9}
-        if args.workload in ("c2", "default", "fft1024_u8"):
-            cpu["optimised_cpu"] = numpy_fft_line(threads)
 
     if rank == 0:
         cfg = config_dict(args.workload)
