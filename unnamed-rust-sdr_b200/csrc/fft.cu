@@ -767,6 +767,13 @@ __global__ void __launch_bounds__(256, 4) fft_l2_kernel(FftArgs a, int lag, long
     }
 }
 
+// MEASURED AND REMOVED (round 2): a software-prefetching variant of fft_l2_kernel -- tickets requested two ahead, the next
+// item's 16 elements per thread loaded into registers while the current item is computed (STEP 1 items only when their
+// transform's counter already reads complete) -- at 120 registers and therefore 2 CTAs per SM instead of 4.  Correct (the
+// FFT suite passed) and SLOWER on every size: 180 / 177 / 170 vs 228 / 220 / 213 Gsamples/s at n = 2^14 / 2^15 / 2^16, A/B on
+// one box (profiles/r02_ab_tma.txt).  ncu on the kernel below (profiles/r02_ncu_fft_l2_64k.txt): barrier stalls 6.5 and
+// long-scoreboard 3.1 cycles per issue, issue 44 %, L2 44 %, DRAM 43 %: what hides the loads here is the OTHER CTAs of the
+// SM, and halving their number costs more than the prefetch gains.
 template <int LOGN2, int FMT>
 int launch_l2(const FftArgs &a, cudaStream_t st) {
     using PL = L2Plan<LOGN2>;
@@ -785,6 +792,13 @@ int launch_l2(const FftArgs &a, cudaStream_t st) {
     e = cudaMemsetAsync(a.work, 0, (size_t)(a.batches + 1) * sizeof(int), st);
     if (e != cudaSuccess) return cuda_status(e);
     const long long ctas = total < resident ? total : resident;
+    // FORWARD PROGRESS: a STEP 1 item spins on a counter that STEP 0 items of the same transform bump; tickets are handed
+    // out in order, so the wait ends iff every CTA that holds an earlier ticket is RUNNING -- i.e. the grid must not
+    // exceed what the device keeps resident at once (occupancy x SMs, queried above for this kernel and shared-memory
+    // size).  Under MPS with an active-thread-percentage limit, or a partitioned GPU that reports more SMs than it gives
+    // this process, that premise fails; SDR_FFT_NO_L2=1 then selects the two-launch four-step (launch_big), which has
+    // no inter-CTA wait at all.
+    if (ctas > resident || ctas < 1) return SDR_ERR_UNSUPPORTED;
     kern<<<(unsigned)ctas, 256, smem, st>>>(a, lag, total);
     count_launch();
     return launch_status();
@@ -868,6 +882,11 @@ inline int l2_min_logn() {
     return v;
 }
 
+inline bool no_l2() {
+    static const bool v = std::getenv("SDR_FFT_NO_L2") != nullptr;
+    return v;
+}
+
 template <int FMT>
 int launch_fmt(const FftArgs &a, cudaStream_t st) {
     switch (a.log_n) {
@@ -888,13 +907,13 @@ int launch_fmt(const FftArgs &a, cudaStream_t st) {
             if (a.work && !(a.flags & SDR_FFT_RFFT) && l2_min_logn() <= 13) return launch_l2<5, FMT>(a, st);
             return launch_reg2<13, FMT>(a, st);
         case 14:
-            if (a.work && !(a.flags & SDR_FFT_RFFT)) return launch_l2<6, FMT>(a, st);
+            if (a.work && !(a.flags & SDR_FFT_RFFT) && !no_l2()) return launch_l2<6, FMT>(a, st);
             return launch_cta<14, FMT>(a, st);
         case 15:
-            if (a.work && !(a.flags & SDR_FFT_RFFT)) return launch_l2<7, FMT>(a, st);
+            if (a.work && !(a.flags & SDR_FFT_RFFT) && !no_l2()) return launch_l2<7, FMT>(a, st);
             return launch_big<FMT>(a, st);
         case 16:
-            if (a.work && !(a.flags & SDR_FFT_RFFT)) return launch_l2<8, FMT>(a, st);
+            if (a.work && !(a.flags & SDR_FFT_RFFT) && !no_l2()) return launch_l2<8, FMT>(a, st);
             return launch_big<FMT>(a, st);
     }
     return SDR_ERR_UNSUPPORTED;
