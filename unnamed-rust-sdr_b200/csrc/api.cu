@@ -1391,27 +1391,30 @@ static int src_fast_run(sdr_src *s, const SrcLaunch &L, cudaStream_t st) {
         s->fast_tab_stride = one.size();
         s->fast_S = (int)S; s->fast_Kb = Kb; s->fast_ns = ns; s->fast_ratio = ratio;
     }
-    const int hl = (Kb + 2 + 1) & ~1;                       // history region in front of each plane (even: planes stay 16-byte aligned)
-    const long long pitch = ((long long)hl + L.n_out + 7) & ~7LL;
-    int rc = s->fast_planes.reserve((size_t)S * pitch * sizeof(float2));
-    if (rc) return rc;
-    float *planes = (float *)s->fast_planes.p;
-    rc = src_fast_gather(L.v, L.have, P, L.wc + 1, (int)S, planes, pitch, hl, L.n_out, st);
-    if (rc) return rc;
-    for (long long b = 0; b < S; ++b) {
-        FirArgs a;
-        a.in = planes + 2 * (b * pitch + hl);
-        a.hist = planes + 2 * (b * pitch);
-        a.out = L.out;
-        a.taps = nullptr;
-        a.n_in = L.n_out; a.in_stride = L.n_out; a.out_stride = L.n_out; a.hist_stride = hl; a.n_out = L.n_out;
-        a.first = 0;
-        a.K = Kb; a.Kp = Kb; a.HL = hl; a.D = 1; a.n_ch = 1;
-        a.accumulate = b > 0;
-        rc = fir_umma_c64_launch(a, ns, s->d_fast_tab + (size_t)b * s->fast_tab_stride, st);
-        if (rc) return rc;   // (UNSUPPORTED cannot happen after branch 0 went through: same geometry)
+    const long long opitch = (L.n_out + 7) & ~7LL;           // branch outputs (S > 1): rows of opitch frames
+    int rc = SDR_OK;
+    float *bout = nullptr;
+    if (S > 1) {
+        rc = s->fast_planes.reserve((size_t)S * opitch * sizeof(float2));
+        if (rc) return rc;
+        bout = (float *)s->fast_planes.p;
     }
-    return SDR_OK;
+    // ONE launch: the S phase planes are S "channels" with their own taps, gathered by the kernel's producers straight from
+    // the handle's frames (x_s[u] = v[S u + P + W - s]); every CTA is bound to one branch (one table in shared memory) and
+    // the S * ceil(n_out / 4096) tiles spread over the SMs (11 waves for C3 instead of 5 launches x 3)
+    FirArgs a;
+    a.in = L.v;
+    a.hist = L.v;
+    a.out = S > 1 ? bout : L.out;
+    a.taps = nullptr;
+    a.n_in = L.n_out; a.in_stride = 0; a.out_stride = opitch; a.hist_stride = 0; a.n_out = L.n_out;
+    a.first = 0;
+    a.K = Kb; a.Kp = Kb; a.HL = 0; a.D = 1; a.n_ch = (int)S;
+    a.in_step = S; a.in_off = P + L.wc + 1; a.in_limit = L.have;
+    rc = fir_umma_c64_launch(a, ns, s->d_fast_tab, st, S > 1 ? (long long)s->fast_tab_stride : 0);
+    if (rc) return rc;
+    if (S > 1) rc = src_fast_sum(bout, opitch, (int)S, L.out, L.n_out, st);
+    return rc;
 }
 
 static int src_process_impl(sdr_src *s, SDR_SRC_DATA *d, bool dev_ptrs) {

@@ -62,6 +62,9 @@ struct UcArgs {
     int plane_bytes;     // 2 * nel rounded up to 1024 (swizzle period)
     int stages;
     int nraw;            // raw ring slots: 2 = the next tile's window lands while this one is converted, 1 = after it
+    // per-channel taps (the polyphase branches of the rational resampler): channel c filters with the table at
+    // tab + c * tab_stride, and every CTA is bound to ONE channel (c = blockIdx.x mod n_ch) so that it loads one table
+    long long tab_stride; // 0 = all channels share `tab`
 };
 
 // ---- PTX wrappers (same conventions as fir_umma.cu) ----------------------------------------------------------------
@@ -183,9 +186,16 @@ __global__ void __launch_bounds__(UC_THREADS, 1) fir_umma_c64_kernel(const UcArg
     auto acce_bar = [&](int s) { return bar0 + 8u * (2 * UC_MAX_STAGES + 2 + s); };
     auto raw_bar = [&](int s) { return bar0 + 8u * (2 * UC_MAX_STAGES + 4 + s); };
 
+    // work items.  Shared taps: item w = ch * ntiles + tile, CTA b takes w = b, b + grid, ...  Per-channel taps: CTA b is
+    // bound to channel b mod n_ch and takes that channel's tiles i, i + cpc, ... (i = b div n_ch, cpc = CTAs on the channel)
+    const bool bound = a.tab_stride != 0;
+    const int my_ch = bound ? (int)(blockIdx.x % f.n_ch) : -1;
+    const long long w_begin = bound ? (long long)(blockIdx.x / f.n_ch) : (long long)blockIdx.x;
+    const long long w_step = bound ? (long long)((gridDim.x - my_ch + f.n_ch - 1) / f.n_ch) : (long long)gridDim.x;
+    const long long w_end = bound ? (long long)a.ntiles : (long long)a.ntiles * f.n_ch;
     // ---- one-time setup ----
     {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.tab);
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.tab + (bound ? (long long)my_ch * a.tab_stride : 0LL));
         uint4 *dst = reinterpret_cast<uint4 *>(gen + (size_t)NST * SB);
         for (int i = tid; i < KS * NCOL * 2; i += UC_THREADS) dst[i] = __ldg(src + i);
     }
@@ -205,12 +215,13 @@ __global__ void __launch_bounds__(UC_THREADS, 1) fir_umma_c64_kernel(const UcArg
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
 
-    const long long nwork = (long long)a.ntiles * f.n_ch;
-    const long long wstride = gridDim.x;
+    const long long nwork = w_end;
+    const long long wstride = w_step;
     // first raw sample of tile wt (in the channel's input coordinates): 16-byte aligned address by choice of delta
     auto tile_s0 = [&](long long wt) { return wt * (long long)UC_TILE - (f.K - 1) - a.delta; };
     auto split = [&](long long w, int &ch, long long &wt) {
-        if (f.n_ch == 1) { ch = 0; wt = w; }
+        if (bound) { ch = my_ch; wt = w; }
+        else if (f.n_ch == 1) { ch = 0; wt = w; }
         else { ch = (int)(w / a.ntiles); wt = w - (long long)ch * a.ntiles; }
     };
 
@@ -220,9 +231,10 @@ __global__ void __launch_bounds__(UC_THREADS, 1) fir_umma_c64_kernel(const UcArg
         // Elements [e_lo, e_hi) of a tile's window are real input samples at 16-byte aligned addresses: ONE bulk copy.
         // What is left -- carried history / zeros in front of the stream (fir.rs:15), zeros behind its end, at most one
         // odd sample at either side -- is a few hundred elements of the first and last tile of a channel: plain stores.
+        const bool gather = f.in_step != 0;
         auto tma_range = [&](long long w, int &e_lo, int &e_hi) {
             e_lo = e_hi = 0;
-            if (w >= nwork) return;
+            if (w >= nwork || gather) return;
             int ch; long long wt;
             split(w, ch, wt);
             const long long s0 = tile_s0(wt);
@@ -243,17 +255,33 @@ __global__ void __launch_bounds__(UC_THREADS, 1) fir_umma_c64_kernel(const UcArg
             mbar_arrive_expect_tx(raw_bar(slot), bytes);
             tma_bulk_g2s(raw_s + (uint32_t)slot * RAWB + 8u * (uint32_t)e_lo, src, bytes, raw_bar(slot));
         };
-        if (ptid == 0) issue_tma(blockIdx.x, 0);
+        if (ptid == 0) issue_tma(w_begin, 0);
         const bool two = a.nraw == 2;
         int stage = 0, slot = 0;
         uint32_t ph = 0, rph[UC_RAW] = {0, 0};
-        for (long long w = blockIdx.x; w < nwork; w += wstride) {
+        for (long long w = w_begin; w < nwork; w += wstride) {
             // the next tile's window goes into the other slot (last read one iteration ago, before the closing barrier)
             if (two && ptid == 0) issue_tma(w + wstride, slot ^ 1);
             uint8_t *rs = raw_g + (size_t)slot * RAWB;
             int e_lo, e_hi;
             tma_range(w, e_lo, e_hi);
-            if (e_hi - e_lo < NEL) {
+            if (gather) {
+                // polyphase branch of the resampler: the window is a strided view of the caller's frames (every in_step-th
+                // frame from in_off - ch), zero outside them.  8-byte loads at a 8 in_step-byte stride: the other
+                // branches' CTAs read the neighbouring frames of the same sectors, so HBM still sees every frame once
+                int ch; long long wt;
+                split(w, ch, wt);
+                const long long j0 = f.in_step * tile_s0(wt) + f.in_off - ch;
+                const float2 *in = (const float2 *)f.in;
+#pragma unroll 4
+                for (int e = ptid; e < NEL; e += 32 * UC_PROD_WARPS) {
+                    const long long j = j0 + f.in_step * e;
+                    float2 v = make_float2(0.0f, 0.0f);
+                    if (j >= 0 && j < f.in_limit) v = __ldg(in + j);
+                    *reinterpret_cast<float2 *>(rs + 8 * e) = v;
+                }
+                prod_bar_sync();
+            } else if (e_hi - e_lo < NEL) {
                 int ch; long long wt;
                 split(w, ch, wt);
                 const long long s0 = tile_s0(wt);
@@ -308,7 +336,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) fir_umma_c64_kernel(const UcArg
         const uint64_t bdesc0 = smem_desc(tab_s, 128, 256, 0);
         int stage = 0, as = 0;
         uint32_t ph = 0, aph = 0;
-        for (long long w = blockIdx.x; w < nwork; w += wstride) {
+        for (long long w = w_begin; w < nwork; w += wstride) {
             mbar_wait(full_bar(stage), ph);
             mbar_wait(acce_bar(as), aph ^ 1u);
             tc_fence_after();
@@ -349,7 +377,7 @@ __global__ void __launch_bounds__(UC_THREADS, 1) fir_umma_c64_kernel(const UcArg
         const int quad = warp & 3;  // TMEM lane quadrant this warp may access
         uint32_t aph = 0;
         long long it = 0;
-        for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
+        for (long long w = w_begin; w < nwork; w += wstride, ++it) {
             if ((it & 1) != g) continue;
             int ch; long long wt;
             split(w, ch, wt);
@@ -472,11 +500,12 @@ bool fir_umma_c64_build_tables(const float *taps, int K, int ns, std::vector<uin
 }
 
 // returns SDR_ERR_UNSUPPORTED when this path does not apply to the call (caller falls back to the CUDA-core kernels)
-int fir_umma_c64_launch(const FirArgs &f, int ns, const uint8_t *d_tables, cudaStream_t st) {
+int fir_umma_c64_launch(const FirArgs &f, int ns, const uint8_t *d_tables, cudaStream_t st, long long branch_tab_stride) {
     if (f.n_out <= 0) return SDR_OK;
     if (f.D != 1 || !fir_umma_c64_applies(f.K, f.D, false, ns)) return SDR_ERR_UNSUPPORTED;
-    if (((uintptr_t)f.in & 7) || ((uintptr_t)f.out & 15) || ((uintptr_t)f.hist & 7) ||
-        (f.n_ch > 1 && ((f.in_stride & 1) || (f.out_stride & 1))))
+    const bool gather = f.in_step != 0;
+    if (((uintptr_t)f.in & 7) || ((uintptr_t)f.out & 15) || (!gather && ((uintptr_t)f.hist & 7)) ||
+        (f.n_ch > 1 && ((!gather && (f.in_stride & 1)) || (f.out_stride & 1))))
         return SDR_ERR_UNSUPPORTED;
     const int KS = uc_ksteps(f.K);
     int stages = 2, nraw = 1;
@@ -492,11 +521,14 @@ int fir_umma_c64_launch(const FirArgs &f, int ns, const uint8_t *d_tables, cudaS
     // sample -(K-1) - delta of a tile must sit at a 16-byte aligned address: 8-byte samples, so delta is 0 or 1
     long long d = ((long long)(((uintptr_t)f.in >> 3) & 1) - (long long)(f.K - 1)) % 2;
     if (d < 0) d += 2;
+    if (gather) d = 0;  // no bulk copy, no alignment to keep
     a.delta = (int)d;
     a.tab = d_tables + (size_t)d * KS * 32 * ns * 32;
+    a.tab_stride = branch_tab_stride;
     a.ntiles = (int)((f.n_out + UC_TILE - 1) / UC_TILE);
     const int sms = current_sm_count();
     const long long nwork = (long long)a.ntiles * f.n_ch;
+    if (branch_tab_stride && f.n_ch > sms) return SDR_ERR_UNSUPPORTED;  // every channel needs a CTA of its own
     const unsigned grid = (unsigned)std::min<long long>(nwork, sms);
     auto go = [&](auto kern) -> int {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

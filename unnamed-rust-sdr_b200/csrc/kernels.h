@@ -15,7 +15,10 @@ struct FirArgs {
     long long n_in, in_stride, out_stride, hist_stride, n_out;
     long long first;   // index (in new-input coordinates) of the first kept output
     int K, Kp, HL, D, n_ch;
-    int accumulate = 0;  // c64 tcgen05 kernel only: out += result (the polyphase branches of the rational resampler)
+    int accumulate = 0;  // c64 tcgen05 kernel only: out += result
+    // c64 tcgen05 kernel only, gather mode (the polyphase branches of the rational resampler): when in_step != 0, sample u
+    // of channel c is in[in_step * u + in_off - c] for indices inside [0, in_limit) and zero outside (no hist, no strides)
+    long long in_step = 0, in_off = 0, in_limit = 0;
 };
 // fmt: sdr_format_t.  Picks the register-blocked kernel when D == 1 and alignment allows,
 // the generic one otherwise.  *path: 1 = direct (FMA), 2 = strict order.
@@ -51,7 +54,9 @@ int fir_umma_launch(const FirArgs &a, int R, int PC, int mode, const uint8_t *d_
 // ns = 3 (six products, f32-grade accuracy) or 2 (three products, < 1e-5 of max|y|)
 bool fir_umma_c64_applies(int K, int D, bool taps_complex, int ns);
 bool fir_umma_c64_build_tables(const float *taps, int K, int ns, std::vector<uint8_t> &out);
-int fir_umma_c64_launch(const FirArgs &a, int ns, const uint8_t *d_tables, cudaStream_t st);
+// branch_tab_stride != 0: channel c uses the table set at d_tables + c * branch_tab_stride (per-channel taps; every CTA is
+// bound to one channel, n_ch <= SM count)
+int fir_umma_c64_launch(const FirArgs &a, int ns, const uint8_t *d_tables, cudaStream_t st, long long branch_tab_stride = 0);
 
 // ---------------------------------------------------------------------------------------
 // FFT (fft.cu)
@@ -140,12 +145,12 @@ struct SrcLaunch {
 int src_launch(const SrcLaunch &s, cudaStream_t st);
 // Rational-ratio sinc conversion as a polyphase decimating FIR on the tensor cores (integer step S = 1/ratio, integer
 // positions, 2 channels = one c64 stream): y[m] = sum_s FIR_{g_s}(x_s)[m], x_s[u] = v[S u + P + W - s], g_s[t] = g[S t + s],
-// g[k] = rho * coef(|W - k|), W = wc + 1.  src_fast_taps fills the S branch filters (each Kb taps, zero padded);
-// src_fast_gather writes the S phase planes (hl zero / history elements, then n_out elements each, pitch plane_pitch).
+// g[k] = rho * coef(|W - k|), W = wc + 1.  src_fast_taps fills the S branch filters (each Kb taps, zero padded); the FIR
+// kernel gathers x_s itself (FirArgs::in_step).
 int src_fast_branch_len(long long wc, int S);
 void src_fast_taps(int type, double ratio, int S, std::vector<float> &branches);
-int src_fast_gather(const float *v, long long have, long long P, long long W, int S, float *planes, long long plane_pitch,
-                    int hl, long long n_out, cudaStream_t st);
+// out[m] = ((b_0[m] + b_1[m]) + b_2[m]) + ... over the S branch outputs (rows of `pitch` frames)
+int src_fast_sum(const float *branches, long long pitch, int S, float *out, long long n_out, cudaStream_t st);
 // the windowed-sinc half table of converter `type` (0..2), computed once on the host in f64
 size_t src_sinc_table_host(int type, const float **table, int *increment);
 double src_sinc_wing(int type, double ratio, double *rq, double *rho, long long *wc);

@@ -552,23 +552,31 @@ void src_fast_taps(int type, double ratio, int S, std::vector<float> &branches) 
     }
 }
 
-// planes[s][hl + u] = v[S u + P + W - s] (frame = one c64), zero outside [0, have); u = -hl .. n_out - 1
-__global__ void src_fast_gather_kernel(const float2 *__restrict__ v, long long have, long long base, int S,
-                                       float2 *__restrict__ planes, long long pitch, int hl, long long n_out) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int s = blockIdx.y;
-    if (i >= n_out + hl) return;
-    const long long j = (long long)S * (i - hl) + base - s;
-    float2 x = make_float2(0.0f, 0.0f);
-    if (j >= 0 && j < have) x = __ldg(v + j);
-    planes[(long long)s * pitch + i] = x;
+__global__ void src_fast_sum_kernel(const float2 *__restrict__ br, long long pitch, int S, float2 *__restrict__ out, long long n_out) {
+    // two frames (16 bytes) per thread; the last thread takes the odd frame alone
+    const long long i = 2 * ((long long)blockIdx.x * blockDim.x + threadIdx.x);
+    if (i >= n_out) return;
+    if (i + 1 < n_out) {
+        float4 acc = __ldg(reinterpret_cast<const float4 *>(br + i));
+        for (int s = 1; s < S; ++s) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(br + (long long)s * pitch + i));
+            acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+        }
+        *reinterpret_cast<float4 *>(out + i) = acc;
+    } else {
+        float2 acc = __ldg(br + i);
+        for (int s = 1; s < S; ++s) {
+            const float2 v = __ldg(br + (long long)s * pitch + i);
+            acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
+        }
+        out[i] = acc;
+    }
 }
 
-int src_fast_gather(const float *v, long long have, long long P, long long W, int S, float *planes, long long plane_pitch,
-                    int hl, long long n_out, cudaStream_t st) {
-    const long long per = n_out + hl;
-    dim3 grid((unsigned)((per + 255) / 256), (unsigned)S);
-    src_fast_gather_kernel<<<grid, 256, 0, st>>>((const float2 *)v, have, P + W, S, (float2 *)planes, plane_pitch, hl, n_out);
+// pitch (frames) even and the rows / out 16-byte aligned
+int src_fast_sum(const float *branches, long long pitch, int S, float *out, long long n_out, cudaStream_t st) {
+    const long long nt = (n_out + 1) / 2;
+    src_fast_sum_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>((const float2 *)branches, pitch, S, (float2 *)out, n_out);
     count_launch();
     return launch_status();
 }
