@@ -125,6 +125,7 @@ def config_dict(name):
         "c1c": ("fir64c_d1_u8iq_2p26", "fused u8-IQ unpack + 64-tap complex FIR, decimation 1", 1 << 26),
         "c3": ("fir255_d10_u8iq_2p26", "fused u8-IQ unpack + 255-tap real FIR, decimation 10", 1 << 26),
         "fir255_u8": ("fir255_d1_u8iq_2p26", "fused u8-IQ unpack + 255-tap real FIR, decimation 1", 1 << 26),
+        "c3_2p28": ("fir255_d10_u8iq_2p28", "fused u8-IQ unpack + 255-tap real FIR, decimation 10", 1 << 28),
         "c3chain": ("c3_chain_fir255_d10_sincbest_2p26", "u8 IQ -> 255-tap FIR /10 -> SampleRate x0.2 (sincbest), device resident", 1 << 26),
         "c4": ("c4_channelizer_128ch_2p16", "128 channels x (255-tap FIR + PLL)", 128 << 16),
         "c4_1024": ("c4_channelizer_1024ch_2p16", "1024 channels x (255-tap FIR + PLL), channels split over the GPUs", 1024 << 16),
@@ -234,7 +235,7 @@ def cpu_leg(name):
         return _cpu_fir_u8(64, 1, False), 1 << 24
     if key == "c1c":
         return _cpu_fir_u8(64, 1, True), 1 << 24
-    if key in ("c3", "c3chain", "c3chain_linear", "c3chain_fastest"):
+    if key in ("c3", "c3_2p28", "c3chain", "c3chain_linear", "c3chain_fastest"):
         return _cpu_fir_u8(255, 10, False), 1 << 24
     if key == "fir255_u8":
         return _cpu_fir_u8(255, 1, False), 1 << 24
@@ -595,6 +596,8 @@ def make_workload(name, cx):
         return wl_fir_u8(cx, "c1c", 64, 1, complex_taps=True)
     if name in ("c3", "fir255_d10_u8"):
         return wl_fir_u8(cx, "c3", 255, 10)
+    if name == "c3_2p28":
+        return wl_fir_u8(cx, "c3_2p28", 255, 10, log2_samples=28)
     if name == "c3chain":
         return wl_c3_chain(cx)
     if name == "c3chain_linear":

@@ -793,6 +793,16 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_planar_kernel(const Um
 // N = 48), all accumulating into the same TMEM columns, and EVERY computed output is kept.  MMA operand traffic per
 // input sample drops from 33 to 16 bytes, the kept-output test disappears from the epilogue.
 // =====================================================================================================================
+// MEASURED AND REMOVED (round 2): the same kernel with window rows 16 outputs apart (32-byte pitch = SWIZZLE_32B, N = 96: the
+// same 30 MMAs produce 2048 outputs instead of 1024 -- half the tensor time per output, half the hand-overs), tables doubled,
+// the raw ring dropped for room (producers LDG.128 their unit one tile ahead into registers).  Correct (bit-identical
+// integer sums, the whole FIR suite passed) and NOT faster: 930 vs 1035 Gsamples/s at 2^26 samples (22 tiles per SM: ramp and
+// tail weigh more with larger tiles), 1142 vs 1160 at 2^28 -- both kernels saturate at ~0.49 of the roofline there, so the MMA
+// count is not what bounds C3.  ncu: the producers wait for their own loads (15 % of all stall samples on the first PRMT
+// behind the LDGs): one tile of loads in flight per SM (42 KB / ~2.6 us) is what Little's law gives for the observed
+// 2.3 TB/s of reads.  A second register set (two tiles ahead) spilled at the 104-register budget of 608 threads and was
+// slower still (749); an L2 prefetch two tiles ahead changed nothing.  What this kernel family needs for C3 is more bytes
+// in flight per SM, i.e. a deeper raw ring, which the 92 KB of N = 96 tables leave no shared memory for.
 constexpr int UP_TILE_OUT = 1024;  // outputs per tile = 128 rows x 8
 constexpr int UP_SETS = 4;         // accumulator sets of 48 TMEM columns
 constexpr int UP_RAW = 3;          // raw ring slots: cp.async runs 2 tiles ahead (deeper rings measured no better)
