@@ -14,6 +14,7 @@
 //                      FFTs with the W_n^{k r} twiddle folded into the load.  The intermediate is
 //                      written in place in the output buffer.
 #include <cstdlib>
+#include <cuda.h>  // CUtensorMap and the cuTensorMapEncodeTiled prototype only: the entry point is resolved at run time
 
 #include "kernels.h"
 
@@ -804,6 +805,476 @@ int launch_l2(const FftArgs &a, cudaStream_t st) {
     return launch_status();
 }
 
+// ---- n = 2^14 .. 2^16, round 2: the same L2-resident four-step with WARP-PRIVATE work items -----------------------
+// ncu on fft_l2_kernel: barrier stalls 6.5 cycles per issue -- four CTA-wide barriers per 4096-element item, each waiting
+// for the slowest warp's loads.  Here an item is 1024 elements owned by ONE warp (the fft1024_warp_kernel recipe): 32
+// points per lane, a radix-32 pass in registers, one exchange through warp-private padded shared memory, a radix-LJ pass,
+// so the only synchronisation is __syncwarp().  n = La * Lb (128 x 128, 256 x 128, 256 x 256):
+//   STEP 0 (transform b, tile s): NCW adjacent columns of the [La][Lb] view; La-point FFT down each; result row-major
+//          scratch[c La + ka] in the OUTPUT buffer.
+//   STEP 1 (transform b, tile s): NCW adjacent columns ka of the [Lb][La] view of the scratch, element (c, ka) times
+//          W_n^{c ka}; Lb-point FFT down each; bin kb is X[ka + La kb].  Same address set in and out: in place.
+// A column of L = 32 LJ points is held by LJ lanes (LJ = 8: 4 columns per warp, LJ = 4: 8 columns per warp); lane
+// (j, cl) = (lane / NCW, lane % NCW) loads rows j + LJ e (e < 32) of column cl -- every load and store instruction
+// covers whole 32-byte sectors (NCW adjacent c64) -- and
+//   X[k1 + 32 k2] = sum_j W_LJ^{j k2} W_L^{j k1} sum_e W_32^{e k1} x[j + LJ e].
+// Items are assigned STATICALLY: in round r warp w takes item r W + ((w + rot_r) mod W) of the same wave order as above
+// (STEP 0 of transform g, STEP 1 of transform g - lag); rot_r makes every warp alternate between the two (cheaper /
+// dearer) steps.  A STEP 1 item acquire-spins on its transform's counter.  Forward progress: every warp walks its items
+// in increasing global order and all warps are resident (grid = occupancy x SMs, checked by the launcher), so the
+// lowest unfinished item always belongs to a running warp whose dependencies (lower items) are complete.
+template <int LJ> struct ColPlan {
+    static constexpr int NCW = 32 / LJ, NB = 32 / LJ;  // L = 32 LJ points per column
+    static constexpr int SK = LJ + 1;                 // exchange: element (cl, k1, j) at cl SC + k1 SK + j
+    static constexpr int SC = LJ == 8 ? 292 : 162;    // both the k1-major writes and the j-major reads conflict free
+    static constexpr int XCH = NCW * SC;              // float2 per warp
+};
+
+// in: v[e] = x[j + LJ e]; out: v[i + NB k2] = X[(j + LJ i) + 32 k2]
+template <int LJ, bool PK>
+__device__ __forceinline__ void col_fft(float2 (&v)[32], float2 *xch, const float2 *twl, int j, int cl) {
+    using CP = ColPlan<LJ>;
+    float2 w[32];
+    dft32<PK>(v, w);
+#pragma unroll
+    for (int k1 = 1; k1 < 32; ++k1) w[k1] = cmul(w[k1], twl[k1 * LJ + j]);
+    float2 *wr = xch + cl * CP::SC + j;
+#pragma unroll
+    for (int k1 = 0; k1 < 32; ++k1) wr[k1 * CP::SK] = w[k1];
+    __syncwarp();
+    const float2 *rd = xch + cl * CP::SC + j * CP::SK;
+#pragma unroll
+    for (int i = 0; i < CP::NB; ++i)
+#pragma unroll
+        for (int jp = 0; jp < LJ; ++jp) v[i + CP::NB * jp] = rd[i * LJ * CP::SK + jp];
+    __syncwarp();  // the exchange buffer may be rewritten by this warp's next item
+#pragma unroll
+    for (int i = 0; i < CP::NB; ++i) dft<LJ, CP::NB, PK>(v + i);
+}
+
+template <int LOGN> struct L2WPlan {
+    static constexpr int LJA = LOGN == 14 ? 4 : 8, LJB = LOGN == 16 ? 8 : 4;
+    static constexpr int LA = 32 * LJA, LB = 32 * LJB, S = (1 << LOGN) / 1024;
+    static constexpr int WARPS = 8;
+    static constexpr int XCH = ColPlan<LJA>::XCH > ColPlan<LJB>::XCH ? ColPlan<LJA>::XCH : ColPlan<LJB>::XCH;
+    static constexpr size_t smem_bytes() { return (size_t)(WARPS * XCH + 32 * LJA + 32 * LJB) * sizeof(float2); }
+};
+
+template <int LOGN, int FMT>
+__global__ void __launch_bounds__(256, 2) fft_l2w_kernel(FftArgs a, int lag, long long total_items) {
+    using PL = L2WPlan<LOGN>;
+    constexpr int LJA = PL::LJA, LJB = PL::LJB, LA = PL::LA, LB = PL::LB, S = PL::S, n = 1 << LOGN;
+    constexpr int NCWA = 32 / LJA, NCWB = 32 / LJB;
+    constexpr bool PK = true;
+    extern __shared__ float4 smem4[];
+    float2 *sm = reinterpret_cast<float2 *>(smem4);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float2 *xch = sm + warp * PL::XCH;
+    float2 *twa = sm + PL::WARPS * PL::XCH;  // W_La^{j k1} at [k1 LJA + j]
+    float2 *twb = twa + 32 * LJA;            // W_Lb^{j k1} at [k1 LJB + j]
+    for (int i = tid; i < 32 * LJA; i += 256) twa[i] = __ldg(a.tw + (long long)((i / LJA) * (i % LJA)) * (n / LA));
+    for (int i = tid; i < 32 * LJB; i += 256) twb[i] = __ldg(a.tw + (long long)((i / LJB) * (i % LJB)) * (n / LB));
+    __syncthreads();
+    int *flags = a.work + 1;
+    const bool norm = (a.flags & SDR_FFT_NORM) != 0;
+    const int half = (a.flags & SDR_FFT_SHIFT) ? LB / 2 : 0;
+    const long long W = (long long)gridDim.x * PL::WARPS;
+    const int w = blockIdx.x * PL::WARPS + warp;
+    const int delta = (int)((((S - W) % (2 * S)) + 2 * S) % (2 * S));
+    int rot = 0;
+    for (long long base = 0; base < total_items; base += W, rot = (rot + delta) % (2 * S)) {
+        long long pos = w + rot;
+        if (pos >= W) pos -= W;
+        const long long item = base + pos;
+        if (item >= total_items) continue;
+        const long long g = item / (2 * S);
+        const int slot = (int)(item % (2 * S));
+        float2 v[32];
+        if (slot < S) {
+            // ------------------------------ STEP 0 ------------------------------
+            const long long b = g;
+            if (b >= a.batches) continue;
+            const int j = lane / NCWA, cl = lane % NCWA;
+            const int c = slot * NCWA + cl;
+            const long long src = b * n + (long long)j * LB + c;
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = load_elem<FMT>(a.in, src + (long long)e * LJA * LB);
+            col_fft<LJA, PK>(v, xch, twa, j, cl);
+            float2 *dst = a.out + b * n + (long long)c * LA + j;
+#pragma unroll
+            for (int i = 0; i < NCWA; ++i)
+#pragma unroll
+                for (int k2 = 0; k2 < LJA; ++k2) dst[LJA * i + 32 * k2] = v[i + NCWA * k2];
+            __syncwarp();  // orders the other lanes' stores before lane 0's fence
+            if (lane == 0) {
+                __threadfence();
+                atomicAdd(flags + b, 1);
+            }
+        } else {
+            // ------------------------------ STEP 1 ------------------------------
+            const long long b = g - lag;
+            if (b < 0 || b >= a.batches) continue;
+            const int j = lane / NCWB, cl = lane % NCWB;
+            const int ka = (slot - S) * NCWB + cl;
+            // twiddle W_n^{ka (j + LJB e)} = w0 p1^e, from two exact table entries by a depth-5 product tree
+            float2 w0 = __ldg(a.tw + ka * j);
+            const float2 p1 = __ldg(a.tw + ka * LJB);
+            if (lane == 0)
+                while (ld_acquire_gpu(flags + b) < S) __nanosleep(64);
+            __syncwarp();  // the acquire above + this barrier order every lane's (L2, .cg) loads after the STEP 0 stores
+            float2 *col = a.out + b * n + ka;
+            {
+                const float2 *src = col + (long long)j * LA;
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = __ldcg(src + (long long)e * LJB * LA);
+            }
+            // 1/sqrt(n) folds into the twiddle exactly when it is a power of two (n = 4^k)
+            const bool fold = norm && (LOGN % 2 == 0);
+            if (fold) { w0.x *= a.norm; w0.y *= a.norm; }
+            {
+                const float2 p2 = cmul(p1, p1), p4 = cmul(p2, p2), p8 = cmul(p4, p4), p16 = cmul(p8, p8);
+                float2 t[32];
+                t[0] = w0; t[1] = cmul(w0, p1);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) t[2 + e] = cmul(t[e], p2);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) t[4 + e] = cmul(t[e], p4);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) t[8 + e] = cmul(t[e], p8);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) t[16 + e] = cmul(t[e], p16);
+#pragma unroll
+                for (int e = 0; e < 32; ++e) v[e] = cmul(v[e], t[e]);
+            }
+            col_fft<LJB, PK>(v, xch, twb, j, cl);
+            const float sc = (norm && !fold) ? a.norm : 1.0f;
+#pragma unroll
+            for (int i = 0; i < NCWB; ++i)
+#pragma unroll
+                for (int k2 = 0; k2 < LJB; ++k2) {
+                    const int kb = (j + LJB * i) + 32 * k2;  // bin ka + La kb
+                    float2 o = v[i + NCWB * k2];
+                    if (LOGN % 2 != 0) { o.x *= sc; o.y *= sc; }
+                    col[(long long)LA * ((kb + half) & (LB - 1))] = o;
+                }
+        }
+    }
+}
+
+template <int LOGN, int FMT>
+int launch_l2w(const FftArgs &a, cudaStream_t st) {
+    using PL = L2WPlan<LOGN>;
+    const size_t smem = PL::smem_bytes();
+    auto kern = fft_l2w_kernel<LOGN, FMT>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    const int sms = current_sm_count();
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem);
+    if (per_sm < 1) return SDR_ERR_UNSUPPORTED;
+    const long long resident = (long long)sms * per_sm;  // every CTA of the grid must be running: see FORWARD PROGRESS above
+    const long long W = resident * PL::WARPS;
+    // a STEP 1 item comes at least one and a half rounds after the STEP 0 items of its transform
+    const int lag = (int)((W * 3 / 2 + 2 * PL::S - 1) / (2 * PL::S)) + 1;
+    const long long total = (a.batches + lag) * 2 * PL::S;
+    e = cudaMemsetAsync(a.work, 0, (size_t)(a.batches + 1) * sizeof(int), st);
+    if (e != cudaSuccess) return cuda_status(e);
+    kern<<<(unsigned)resident, 256, smem, st>>>(a, lag, total);
+    count_launch();
+    return launch_status();
+}
+
+// ---- n = 2^14 .. 2^16, round 2: fft_l2_kernel fed by TMA ----------------------------------------------------------
+// ncu on fft_l2_kernel: barrier 6.5 + long scoreboard 3.1 stall cycles per issue -- every item starts with 16 exposed
+// LDG.64 per thread and the CTA's first barrier waits for the slowest warp's loads.  (A warp-private variant with 32
+// points per lane, fft_l2w_kernel above, removes the barriers but needs rows of 4 adjacent c64 = one 32-byte sector per
+// row and warp: 8 L1 wavefronts per request instead of 2, L1TEX 69 % busy, 165 vs 225 Gsamples/s: kept for the record.)
+// Here the NEXT item's 4096-element tile is copied into a second shared-memory stage by ONE TMA tensor copy
+// (cp.async.bulk.tensor.3d over {columns, rows, transforms}, SASS UTMALDG, issued by one thread, completing in bytes on
+// an mbarrier; first version: 256 bulk row copies of 128 bytes per item -- 27 cycles each in the copy engine, 85
+// Gsamples/s) while the current item is computed:
+// an item's first pass reads shared memory instead of HBM / L2, the same number of issued instructions (LDS for LDG).
+// The consumed stage doubles as the item's exchange buffer.  Items are assigned statically (round it: item
+// it G + ((x + rot_it) mod G), rot_it alternating the two steps on every CTA), so the next item is known without a
+// ticket, and a CTA-wide barrier serves three purposes at once (stage consumed / previous item's stores done -> its
+// counter bump / other stage free for the next copy): two barriers per item instead of four.
+// Forward progress: as for fft_l2w_kernel -- a CTA walks its items in increasing global order, a STEP 1 copy waits only
+// for STEP 0 items at least lag 2S - S items older, and lag 2S > G + 3S makes those older than anything this CTA has
+// not yet signalled; the launcher keeps the whole grid resident.
+__device__ __forceinline__ void tma_tile_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                     : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+}
+
+template <int LOGN2, int FMT>
+__global__ void __launch_bounds__(288, 3) fft_l2t_kernel(FftArgs a, int lag, long long total_items,
+                                                         const __grid_constant__ CUtensorMap map_in,
+                                                         const __grid_constant__ CUtensorMap map_scr) {
+    using PL = L2Plan<LOGN2>;
+    constexpr int N2 = PL::N2, NC = PL::NC, TC = PL::TC, R2 = PL::R2, NB2 = PL::NB2, S = PL::S;
+    constexpr int n = 256 * N2, ES = FmtBytes<FMT>::v;
+    constexpr int STAGE = (PL::SM_ELEMS + 15) & ~15;  // float2 per stage (128-byte multiple)
+    extern __shared__ __align__(128) float4 smem_l2t[];  // TMA tensor copies land on 128-byte boundaries
+    __shared__ __align__(8) uint64_t full_bar[2];
+    __shared__ unsigned cnt[2];
+    float2 *sm = reinterpret_cast<float2 *>(smem_l2t);
+    float2 *tw0 = sm + 2 * STAGE;      // W_256^{q t}, q = 1..15, t < 16
+    float2 *tw1 = tw0 + 15 * 16;       // W_N2^{s k}, s = 1..R2-1, k < 16
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 15 * 16; i += 288) tw0[i] = __ldg(a.tw + (long long)((i / 16 + 1) * (i % 16)) * (n / 256));
+    for (int i = tid; i < (R2 - 1) * 16; i += 288) tw1[i] = __ldg(a.tw + (long long)((i / 16 + 1) * (i % 16)) * 256);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(w1k_smem_u32(&full_bar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(w1k_smem_u32(&full_bar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        cnt[0] = 0;
+        cnt[1] = 0;
+    }
+    __syncthreads();
+    int *flags = a.work + 1;
+    const bool norm = (a.flags & SDR_FFT_NORM) != 0;
+    const int half = (a.flags & SDR_FFT_SHIFT) ? N2 / 2 : 0;
+    const long long G = gridDim.x;
+    const int x = blockIdx.x;
+    const int delta = (int)((((S - G) % (2 * S)) + 2 * S) % (2 * S));
+    const long long n_it = (total_items + G - 1) / G;
+    auto item_at = [&](long long it) -> long long {
+        long long pos = x + (int)((it * delta) % (2 * S));
+        if (pos >= G) pos -= G;
+        return it * G + pos;
+    };
+    // item -> (step, transform, tile); b < 0: nothing to do
+    auto decode = [&](long long item, bool &step1, long long &b, int &tile) {
+        const long long g = item / (2 * S);
+        const int slot = (int)(item % (2 * S));
+        step1 = slot >= S;
+        tile = step1 ? slot - S : slot;
+        b = step1 ? g - lag : g;
+        if (item >= total_items || b >= a.batches) b = -1;
+    };
+    // service lane: copy an item's tile into stage s.  STEP 0 tile: 256 rows x 16 elements of the input; STEP 1 tile:
+    // N2 rows x NC c64 of the scratch, after its transform's STEP 0 items have all signalled (try_only: give up instead
+    // of spinning; returns false when the copy was not issued)
+    auto load_item = [&](long long item, int s, bool try_only) -> bool {
+        bool step1; long long b; int tile;
+        decode(item, step1, b, tile);
+        if (b < 0) return true;
+        const uint32_t bar = w1k_smem_u32(&full_bar[s]), dst = w1k_smem_u32(sm + (size_t)s * STAGE);
+        if (!step1) {
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4096 * ES) : "memory");
+            tma_tile_3d(dst, &map_in, 16 * tile, 0, (int)b, bar);
+        } else {
+            while (ld_acquire_gpu(flags + b) < S) {
+                if (try_only) return false;
+                __nanosleep(64);
+            }
+            // the STEP 0 stores (generic proxy, other SMs; acquired above) before this thread's async-proxy reads of them
+            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4096 * 8) : "memory");
+            tma_tile_3d(dst, &map_scr, NC * tile, 0, (int)b, bar);
+        }
+        return true;
+    };
+    // monotonic shared counters, one release-add per compute warp and item: cnt[0] = "exchange read, the stage is free",
+    // cnt[1] = "stores issued".  (Counters, not barrier phases: the compute warps may run up to two items ahead of the
+    // service lane, which a parity cannot express.)
+    auto cnt_arrive = [&](int which) {
+        __syncwarp();  // orders the other lanes' accesses before lane 0's release
+        if ((tid & 31) == 0)
+            asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(w1k_smem_u32(&cnt[which])) : "memory");
+    };
+    auto cnt_wait = [&](int which, unsigned target) {
+        unsigned v;
+        for (;;) {
+            asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(w1k_smem_u32(&cnt[which])) : "memory");
+            if (v >= target) break;
+            __nanosleep(32);
+        }
+    };
+
+    // ---- service warp (one lane): everything that waits on the memory system without computing -- the TMA issue, the
+    // acquire spin on a STEP 1 item's counter, the release fence + counter bump behind an item's stores.  With thread 0
+    // of the compute warps doing this (first version: 5.5 barrier-stall cycles per issue) seven warps sat at barrier (B)
+    // for the whole of warp 0's fence.  Item it + 2's tile is requested as soon as item it's exchange has been read
+    // (its stage is free): a copy has one and a half items to land.
+    if (tid >= 256) {
+        if (tid != 256) return;
+        load_item(item_at(0), 0, false);
+        if (n_it > 1) load_item(item_at(1), 1, false);
+        unsigned nvalid = 0;
+        for (long long it = 0; it < n_it; ++it) {
+            bool step1; long long b; int tile;
+            decode(item_at(it), step1, b, tile);
+            if (b >= 0) {
+                ++nvalid;
+                cnt_wait(0, 8 * nvalid);
+            }
+            bool issued = true;
+            if (it + 2 < n_it) issued = load_item(item_at(it + 2), (int)(it & 1), true);
+            if (b >= 0 && !step1) {
+                cnt_wait(1, 8 * nvalid);
+                __threadfence();  // cumulative: the CTA's stores of this item (acquired from the warps' release-adds)
+                atomicAdd(flags + b, 1);
+            }
+            if (!issued) load_item(item_at(it + 2), (int)(it & 1), false);
+        }
+        return;
+    }
+    uint32_t ph = 0;        // bit s = parity of stage s's next completion
+    for (long long it = 0; it < n_it; ++it) {
+        const int s = (int)(it & 1);
+        float2 *st = sm + (size_t)s * STAGE;
+        bool step1; long long b; int tile;
+        decode(item_at(it), step1, b, tile);
+        float2 v[16];
+        if (b >= 0) {
+            if (!step1) {
+                mbar_wait_parity(w1k_smem_u32(&full_bar[s]), (ph >> s) & 1u);
+                const int c = tid & 15, rr = tid >> 4;
+                const unsigned char *raw = reinterpret_cast<const unsigned char *>(st);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = raw_elem<FMT>(raw, (rr + 16 * e) * 16 + c);
+            } else {
+                const int c = tid % NC, t = tid / NC;
+                const int k = NC * tile + c;
+                // a_e = W_n^{k (t + e TC)} = w0 * ws^e (the two table loads are in flight while the tile lands)
+                const float2 w0 = __ldg(a.tw + k * t), p1 = __ldg(a.tw + k * TC);
+                mbar_wait_parity(w1k_smem_u32(&full_bar[s]), (ph >> s) & 1u);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = st[(t + TC * e) * NC + c];
+                const float2 p2 = cmul(p1, p1), p4 = cmul(p2, p2), p8 = cmul(p4, p4);
+                float2 tw[16];
+                tw[0] = w0; tw[1] = cmul(w0, p1); tw[2] = cmul(w0, p2); tw[3] = cmul(tw[1], p2);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) tw[4 + e] = cmul(tw[e], p4);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) tw[8 + e] = cmul(tw[e], p8);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) v[e] = cmul(v[e], tw[e]);
+            }
+            ph ^= 1u << s;
+            dft<16, 1, true>(v);
+        }
+        if (b < 0) continue;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // (A) the tile is in registers: the stage becomes the exchange buffer
+        if (!step1) {
+            {
+                const int c = tid & 15, rr = tid >> 4;
+                float2 *dst = st + c * PL::SSTRIDE0;
+#pragma unroll
+                for (int q = 0; q < 16; ++q) dst[17 * rr + q] = v[q];  // pad(16 rr + q) = 17 rr + q
+            }
+            asm volatile("bar.sync 2, 256;" ::: "memory");  // (B) compute warps only
+            const int col = tid >> 4, t = tid & 15;
+            const float2 *srcs = st + col * PL::SSTRIDE0;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = srcs[t + 17 * e];  // pad(t + 16 e) = t + 17 e for t < 16
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // these accesses before the stage's next tensor copy
+            cnt_arrive(0);
+#pragma unroll
+            for (int q = 1; q < 16; ++q) v[q] = cmul(v[q], tw0[(q - 1) * 16 + t]);
+            dft<16, 1, true>(v);
+            float2 *dst = a.out + b * n + 256LL * (16 * tile + col) + t;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) dst[16 * q] = v[q];
+            cnt_arrive(1);
+        } else {
+            const int c = tid % NC, t = tid / NC;
+            const int k = NC * tile + c;
+            float2 *col = st + c * PL::SSTRIDE1;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) col[17 * t + q] = v[q];  // pad(16 t + q) = 17 t + q
+            asm volatile("bar.sync 2, 256;" ::: "memory");  // (B)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[e] = col[pad(t + e * TC)];
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            cnt_arrive(0);
+#pragma unroll
+            for (int vi = 0; vi < NB2; ++vi) {
+                const int kk = (t + vi * TC) & 15;
+#pragma unroll
+                for (int q = 1; q < R2; ++q) v[vi + q * NB2] = cmul(v[vi + q * NB2], tw1[(q - 1) * 16 + kk]);
+            }
+#pragma unroll
+            for (int vi = 0; vi < NB2; ++vi) dft<R2, NB2, true>(v + vi);
+            float2 *ob = a.out + b * n + k;
+#pragma unroll
+            for (int vi = 0; vi < NB2; ++vi)
+#pragma unroll
+                for (int q = 0; q < R2; ++q) {
+                    const int k1 = (t + vi * TC) + 16 * q;  // bin k + 256 k1
+                    float2 o = v[vi + q * NB2];
+                    if (norm) { o.x *= a.norm; o.y *= a.norm; }
+                    ob[256LL * ((k1 + half) & (N2 - 1))] = o;
+                }
+            cnt_arrive(1);
+        }
+    }
+}
+
+// cuTensorMapEncodeTiled, resolved through the runtime (no link-time dependency on libcuda); null = not available
+typedef CUresult (*FftEncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline FftEncodeTiledFn fft_encode_tiled_fn() {
+    static FftEncodeTiledFn fn = []() -> FftEncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        return (FftEncodeTiledFn)p;
+    }();
+    return fn;
+}
+// {cols, rows, transforms} view of `batches` transforms of rows x cols elements of `es` bytes; box = cols_box x rows x 1
+inline bool fft_tile_map(CUtensorMap *tm, const void *base, int es, int cols, int rows, long long batches, int cols_box) {
+    FftEncodeTiledFn enc = fft_encode_tiled_fn();
+    if (!enc) return false;
+    const CUtensorMapDataType dt = es == 8 ? CU_TENSOR_MAP_DATA_TYPE_UINT64 : es == 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : CU_TENSOR_MAP_DATA_TYPE_UINT16;
+    cuuint64_t dims[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)batches};
+    cuuint64_t strides[2] = {(cuuint64_t)cols * es, (cuuint64_t)cols * rows * es};  // bytes, dims 1..2
+    cuuint32_t box[3] = {(cuuint32_t)cols_box, (cuuint32_t)rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int LOGN2, int FMT>
+int launch_l2t(const FftArgs &a, cudaStream_t st) {
+    using PL = L2Plan<LOGN2>;
+    const size_t smem = (size_t)(2 * ((PL::SM_ELEMS + 15) & ~15) + 15 * 16 + (PL::R2 - 1) * 16) * sizeof(float2);
+    auto kern = fft_l2t_kernel<LOGN2, FMT>;
+    CUtensorMap map_in, map_scr;
+    if (!fft_tile_map(&map_in, a.in, FmtBytes<FMT>::v, PL::N2, 256, a.batches, 16) ||
+        !fft_tile_map(&map_scr, a.out, 8, 256, PL::N2, a.batches, PL::NC))
+        return launch_l2<LOGN2, FMT>(a, st);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_status(e);
+    const int sms = current_sm_count();
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 288, smem);
+    if (per_sm < 1) return SDR_ERR_UNSUPPORTED;
+    const long long G = (long long)sms * per_sm;  // the whole grid resident: see FORWARD PROGRESS
+    // a STEP 1 tile is requested one and a half items ahead: three rounds behind its transform's STEP 0 items
+    // (SDR_FFT_L2_LAG = tenths of a round: tuning knob)
+    static const int lag10 = std::getenv("SDR_FFT_L2_LAG") ? std::atoi(std::getenv("SDR_FFT_L2_LAG")) : 30;
+    const int lag = (int)((G * lag10 / 10 + 2 * PL::S - 1) / (2 * PL::S)) + 1;
+    const long long total = (a.batches + lag) * 2 * PL::S;
+    e = cudaMemsetAsync(a.work, 0, (size_t)(a.batches + 1) * sizeof(int), st);
+    if (e != cudaSuccess) return cuda_status(e);
+    kern<<<(unsigned)G, 288, smem, st>>>(a, lag, total, map_in, map_scr);  // 8 compute warps + the service warp
+    count_launch();
+    return launch_status();
+}
+
 // ---- tiny sizes: direct DFT, one thread per output bin ---------------------------------------
 template <int FMT>
 __global__ void fft_naive_kernel(const void *in, float2 *out, const float2 *__restrict__ tw, long long batches,
@@ -886,6 +1357,19 @@ inline bool no_l2() {
     static const bool v = std::getenv("SDR_FFT_NO_L2") != nullptr;
     return v;
 }
+// A/B switch SDR_FFT_L2_MODE: 0 = round 1's ticket kernel (fft_l2_kernel), 1 = warp items (fft_l2w_kernel),
+// 2 = TMA-fed CTA items (fft_l2t_kernel, default)
+inline int l2_mode() {
+    static const int v = std::getenv("SDR_FFT_L2_MODE") ? std::atoi(std::getenv("SDR_FFT_L2_MODE")) : 2;
+    return v;
+}
+template <int LOGN, int FMT>
+int launch_l2_any(const FftArgs &a, cudaStream_t st) {
+    const int mode = l2_mode();
+    if (mode == 1) return launch_l2w<LOGN, FMT>(a, st);
+    if (mode == 2 && (((uintptr_t)a.in) & 15) == 0) return launch_l2t<LOGN - 8, FMT>(a, st);  // bulk copies need 16-byte rows
+    return launch_l2<LOGN - 8, FMT>(a, st);
+}
 
 template <int FMT>
 int launch_fmt(const FftArgs &a, cudaStream_t st) {
@@ -907,13 +1391,16 @@ int launch_fmt(const FftArgs &a, cudaStream_t st) {
             if (a.work && !(a.flags & SDR_FFT_RFFT) && l2_min_logn() <= 13) return launch_l2<5, FMT>(a, st);
             return launch_reg2<13, FMT>(a, st);
         case 14:
-            if (a.work && !(a.flags & SDR_FFT_RFFT) && !no_l2()) return launch_l2<6, FMT>(a, st);
+            if (a.work && !(a.flags & SDR_FFT_RFFT) && !no_l2())
+                return launch_l2_any<14, FMT>(a, st);
             return launch_cta<14, FMT>(a, st);
         case 15:
-            if (a.work && !(a.flags & SDR_FFT_RFFT) && !no_l2()) return launch_l2<7, FMT>(a, st);
+            if (a.work && !(a.flags & SDR_FFT_RFFT) && !no_l2())
+                return launch_l2_any<15, FMT>(a, st);
             return launch_big<FMT>(a, st);
         case 16:
-            if (a.work && !(a.flags & SDR_FFT_RFFT) && !no_l2()) return launch_l2<8, FMT>(a, st);
+            if (a.work && !(a.flags & SDR_FFT_RFFT) && !no_l2())
+                return launch_l2_any<16, FMT>(a, st);
             return launch_big<FMT>(a, st);
     }
     return SDR_ERR_UNSUPPORTED;
