@@ -103,6 +103,11 @@ __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// TMA, non-tensor form: one bulk copy global -> shared, completion (bytes) on an mbarrier.  SASS: UBLKCP.
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
 // TMA tensor copies global -> shared (SASS: UTMALDG), completion in bytes on an mbarrier
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -805,6 +810,7 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_planar_kernel(const Um
 // in flight per SM, i.e. a deeper raw ring, which the 92 KB of N = 96 tables leave no shared memory for.
 constexpr int UP_TILE_OUT = 1024;  // outputs per tile = 128 rows x 8
 constexpr int UP_SETS = 4;         // accumulator sets of 48 TMEM columns
+constexpr int UP_RAW_MODE_DEFAULT = 1;
 constexpr int UP_RAW = 3;          // raw ring slots: cp.async runs 2 tiles ahead (deeper rings measured no better)
 __host__ __device__ constexpr int up_ksteps(int K, int D) { return (7 + (K + 6) / D) / 16 + 1; }
 __host__ __device__ constexpr int up_nsub(int KS) { return 8 * 128 + 16 * KS; }  // sub-samples per plane per tile
@@ -827,11 +833,13 @@ __host__ __device__ constexpr size_t up_smem_bytes(int D, int KS, int stages) {
 constexpr int UP_PROD_WARPS = 8, UP_MMA_WARP = UP_PROD_WARPS, UP_MMA_WARPS = 2, UP_EPI_WARP0 = UP_PROD_WARPS + UP_MMA_WARPS,
               UP_THREADS = (UP_PROD_WARPS + UP_MMA_WARPS + 8) * 32;
 
-template <int D>
+template <int D, int RM>
 __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmArgs a) {
     constexpr int N = 48;
+    // converting producer lanes: in the bulk-copy modes the last producer warp only loads
+    constexpr int NCONV = 32 * (RM ? UP_PROD_WARPS - 1 : UP_PROD_WARPS);
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[2 * UM_STAGES + 2 * UP_SETS];
+    __shared__ __align__(8) uint64_t bars[2 * UM_STAGES + 2 * UP_SETS + 2 * UP_RAW + 1];
     __shared__ uint32_t tmem_base_s;
     const FirArgs &f = a.f;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -847,14 +855,19 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
     auto empty_bar = [&](int s) { return bar0 + 8u * (UM_STAGES + s); };
     auto accf_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + s); };
     auto acce_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + UP_SETS + s); };
-    {
+    auto rawfull_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + 2 * UP_SETS + s); };
+    auto rawfree_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + 2 * UP_SETS + UP_RAW + s); };
+    const uint32_t tab_bar = bar0 + 8u * (2 * UM_STAGES + 2 * UP_SETS + 2 * UP_RAW);
+    if (RM == 0) {
         const uint4 *src = reinterpret_cast<const uint4 *>(a.tab);
         uint4 *dst = reinterpret_cast<uint4 *>(gen + NST * SB);
         for (int i = tid; i < D * KS * N * 2; i += UP_THREADS) dst[i] = __ldg(src + i);
     }
     if (tid == 0) {
-        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full_bar(s), 32 * UP_PROD_WARPS); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full_bar(s), NCONV); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < UP_SETS; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 4); }
+        for (int s = 0; s < UP_RAW; ++s) { mbar_init(rawfull_bar(s), 1); mbar_init(rawfree_bar(s), UP_PROD_WARPS - 1); }
+        mbar_init(tab_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == UP_MMA_WARP) {
@@ -869,7 +882,103 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
     const long long nwork = (long long)a.ntiles * f.n_ch;
     const long long wstride = gridDim.x;
 
-    if (warp < UP_PROD_WARPS) {
+    if (RM != 0 && warp == UP_PROD_WARPS - 1) {
+        // ================= loader warp (bulk-copy modes): raw tiles by TMA bulk copies, UP_RAW tiles ahead =================
+        // The legacy mode gives every lane ITS unit's 16 D contiguous bytes as D 16-byte cp.async: a warp instruction then
+        // touches 32 different 128-byte lines (lane stride 16 D bytes), i.e. 32 L1 tag passes for 512 bytes.  Here the
+        // copy engine moves the tile: ONE bulk copy into a linear slot.  (One copy per skew group of 8 / gcd(D, 8) units,
+        // which keeps the conflict-free skewed layout, was measured far slower: 34 copies of 640 bytes per tile.)
+        const int nunits = NSUB / 8;
+        const int RAWB = (int)up_raw_bytes(D, KS);
+        long long it = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
+            const int slot = (int)(it % UP_RAW);
+            if (it >= UP_RAW) mbar_wait(rawfree_bar(slot), (uint32_t)((it / UP_RAW - 1) & 1));
+            int ch; long long wt;
+            split_work(w, a.ntiles, (int)f.n_ch, ch, wt);
+            const long long w0 = f.first - (f.K - 1) - a.delta + wt * (long long)(UP_TILE_OUT * D);
+            const unsigned char *in = (const unsigned char *)f.in + (long long)ch * f.in_stride * 2;
+            uint8_t *rs = raw0 + (size_t)slot * RAWB;
+            const uint32_t rs_s = smem_u32(rs);
+            // chunks [q_lo, q_hi) of the tile are whole, in-range 16-byte pieces of the input: ONE bulk copy.  The rest
+            // (first / last tile of a channel: carried history, "zero" = byte 128, ragged end) by plain stores.
+            const int nq = nunits * D;
+            long long ql = w0 >= 0 ? 0 : (-w0 + 7) / 8, qh = (f.n_in - w0) / 8;
+            const int q_lo = (int)min(ql, (long long)nq), q_hi = (int)max(min(qh, (long long)nq), (long long)q_lo);
+            const uint32_t bytes = 16u * (uint32_t)(q_hi - q_lo);
+            if (q_lo > 0 || q_hi < nq) {
+                const unsigned char *hist = (const unsigned char *)f.hist + (long long)ch * f.hist_stride * 2;
+                for (int q = lane; q < nq - (q_hi - q_lo); q += 32) {
+                    const int qq = q < q_lo ? q : q + (q_hi - q_lo);
+                    const long long s0 = w0 + 8LL * qq;
+                    if (s0 < f.n_in) {
+                        unsigned short h[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const long long s = s0 + i;
+                            unsigned short x = 0x8080;
+                            if (s >= 0) { if (s < f.n_in) x = *reinterpret_cast<const unsigned short *>(in + 2 * s); }
+                            else if (s >= -(long long)f.HL) x = *reinterpret_cast<const unsigned short *>(hist + 2 * ((long long)f.HL + s));
+                            h[i] = x;
+                        }
+                        uint4 qv;
+                        qv.x = h[0] | ((unsigned)h[1] << 16); qv.y = h[2] | ((unsigned)h[3] << 16);
+                        qv.z = h[4] | ((unsigned)h[5] << 16); qv.w = h[6] | ((unsigned)h[7] << 16);
+                        *reinterpret_cast<uint4 *>(rs + 16 * qq) = qv;
+                    }
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                if (bytes) {
+                    mbar_arrive_expect_tx(rawfull_bar(slot), bytes);
+                    tma_bulk_g2s(rs_s + 16u * (uint32_t)q_lo, in + 2 * (w0 + 8LL * q_lo), bytes, rawfull_bar(slot));
+                } else {
+                    mbar_arrive(rawfull_bar(slot));
+                }
+            }
+        }
+    } else if (RM != 0 && warp < UP_PROD_WARPS) {
+        // ================= converters (bulk-copy modes): raw slot -> D phase planes =================
+        const int ptid = warp * 32 + lane;
+        const int nunits = NSUB / 8;
+        const int RAWB = (int)up_raw_bytes(D, KS);
+        int stage = 0, slot = 0;
+        uint32_t ph = 0, rph = 0;
+        for (long long w = blockIdx.x; w < nwork; w += wstride) {
+            mbar_wait(rawfull_bar(slot), rph);
+            mbar_wait(empty_bar(stage), ph ^ 1u);
+            uint8_t *st_g = gen + (size_t)stage * SB;
+            const uint8_t *rs = raw0 + (size_t)slot * RAWB;
+            for (int v = ptid; v < nunits; v += NCONV) {
+                uint32_t rw[4 * D];
+                const int sk = 0;  // linear slot
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(rs + 16 * (v * D + sk + c));
+                    rw[4 * c] = q.x; rw[4 * c + 1] = q.y; rw[4 * c + 2] = q.z; rw[4 * c + 3] = q.w;
+                }
+#pragma unroll
+                for (int p = 0; p < D; ++p) {
+                    uint32_t o[4];
+#pragma unroll
+                    for (int wd = 0; wd < 4; ++wd) {
+                        const int sa = D * (2 * wd) + p, sb = D * (2 * wd + 1) + p;
+                        const uint32_t sel = (uint32_t)(2 * (sa & 1)) | ((uint32_t)(2 * (sa & 1) + 1) << 4) |
+                                             ((uint32_t)(4 + 2 * (sb & 1)) << 8) | ((uint32_t)(5 + 2 * (sb & 1)) << 12);
+                        o[wd] = __byte_perm(rw[sa >> 1], rw[sb >> 1], sel);
+                    }
+                    *reinterpret_cast<uint4 *>(st_g + (size_t)p * PLB + 16 * v) = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+            fence_proxy_async();
+            mbar_arrive(full_bar(stage));
+            __syncwarp();
+            if (lane == 0) mbar_arrive(rawfree_bar(slot));  // this warp's reads of the slot are done
+            if (++stage == NST) { stage = 0; ph ^= 1u; }
+            if (++slot == UP_RAW) { slot = 0; rph ^= 1u; }
+        }
+    } else if (RM == 0 && warp < UP_PROD_WARPS) {
         // ================= producers: raw ring (cp.async, two tiles ahead) -> D phase planes =================
         const int ptid = warp * 32 + lane;
         const int nunits = NSUB / 8;  // a unit = 8 sub-samples of every phase = D raw chunks = D plane chunks
@@ -966,6 +1075,15 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
         const int mw = warp - UP_MMA_WARP;
         const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         const uint64_t bdesc0 = smem_desc(tab_s, 128, 256, 0);
+        if (RM != 0) {
+            // the tap tables arrive by one bulk copy while the first raw tile is loaded and converted
+            if (mw == 0 && elect_one()) {
+                mbar_arrive_expect_tx(tab_bar, (uint32_t)(D * KS * N * 32));
+                tma_bulk_g2s(tab_s, a.tab, (uint32_t)(D * KS * N * 32), tab_bar);
+            }
+            __syncwarp();
+            mbar_wait(tab_bar, 0);
+        }
         long long it = 0;
         for (long long w = blockIdx.x; w < nwork; w += wstride, ++it) {
             if ((it & (UP_MMA_WARPS - 1)) != mw) continue;
@@ -1247,15 +1365,22 @@ static int fir_umma_poly_launch(const FirArgs &f, const uint8_t *d_tables, const
         count_launch();
         return launch_status();
     };
+    // raw-tile staging: 0 = per-lane cp.async (round 1), 1 = one TMA bulk copy per tile
+    static const int rm_env = []() { const char *e = std::getenv("SDR_UP_RAW"); return e ? std::atoi(e) : UP_RAW_MODE_DEFAULT; }();
+#define SDR_UP_CASE(DD)                                              \
+    case DD:                                                         \
+        if (rm_env == 0) return go(fir_umma_poly_kernel<DD, 0>);     \
+        return go(fir_umma_poly_kernel<DD, 1>);
     switch (D) {
-        case 5: return go(fir_umma_poly_kernel<5>);
-        case 6: return go(fir_umma_poly_kernel<6>);
-        case 7: return go(fir_umma_poly_kernel<7>);
-        case 8: return go(fir_umma_poly_kernel<8>);
-        case 9: return go(fir_umma_poly_kernel<9>);
-        case 10: return go(fir_umma_poly_kernel<10>);
-        case 12: return go(fir_umma_poly_kernel<12>);
+        SDR_UP_CASE(5)
+        SDR_UP_CASE(6)
+        SDR_UP_CASE(7)
+        SDR_UP_CASE(8)
+        SDR_UP_CASE(9)
+        SDR_UP_CASE(10)
+        SDR_UP_CASE(12)
     }
+#undef SDR_UP_CASE
     return SDR_ERR_UNSUPPORTED;
 }
 
