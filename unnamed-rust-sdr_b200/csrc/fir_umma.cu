@@ -810,34 +810,42 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_planar_kernel(const Um
 // in flight per SM, i.e. a deeper raw ring, which the 92 KB of N = 96 tables leave no shared memory for.
 constexpr int UP_TILE_OUT = 1024;  // outputs per tile = 128 rows x 8
 constexpr int UP_SETS = 4;         // accumulator sets of 48 TMEM columns
-constexpr int UP_RAW_MODE_DEFAULT = 1;
 constexpr int UP_RAW = 3;          // raw ring slots: cp.async runs 2 tiles ahead (deeper rings measured no better)
 __host__ __device__ constexpr int up_ksteps(int K, int D) { return (7 + (K + 6) / D) / 16 + 1; }
 __host__ __device__ constexpr int up_nsub(int KS) { return 8 * 128 + 16 * KS; }  // sub-samples per plane per tile
-// A producer lane reads the D raw chunks of ITS unit v (chunks v*D .. v*D + D-1) with LDS.128; for even D the lane stride
-// of 16 D bytes puts the 8 lanes of a quarter warp on 8 / gcd(D, 8) bank groups (2-way conflicts at D = 10, 8-way at
-// D = 8; ncu: 35 % of the kernel's shared wavefronts were replays).  The raw ring is therefore skewed: unit v lives
-// up_skew(D, v) chunks further on.  The same lane writes (cp.async) and reads a unit, so only its own address changes.
-__host__ __device__ constexpr int up_gcd8(int D) { return (D % 8 == 0) ? 8 : (D % 4 == 0) ? 4 : (D % 2 == 0) ? 2 : 1; }
-__host__ __device__ constexpr int up_skew(int D, int v) { return (v * up_gcd8(D)) >> 3; }
-__host__ __device__ constexpr size_t up_raw_bytes(int D, int KS) {
-    return (size_t)D * 2 * up_nsub(KS) + 16 * (size_t)(up_skew(D, up_nsub(KS) / 8) + 1);
-}
+// Raw slots are LINEAR copies of the input (one TMA bulk copy each).  A converter lane reads whole 16-byte chunks of its
+// item with LDS.128; with a lane stride of 16 D bytes (a full unit = D chunks per lane) the 8 lanes of a quarter warp
+// fall on 8 / gcd(D, 8) bank groups.  For D = 2 (mod 4) (C3's D = 10) a lane takes HALF a unit instead (D / 2 chunks,
+// 4 sub-samples of every phase, one 8-byte store per plane): the lane stride of 8 D bytes is an odd multiple of 16 and
+// every quarter warp is conflict free.  (Round 1 skewed the slot instead; a bulk copy cannot skew.)
+__host__ __device__ constexpr bool up_half(int D) { return D % 4 == 2; }
+__host__ __device__ constexpr size_t up_raw_bytes(int D, int KS) { return (size_t)D * 2 * up_nsub(KS); }
 __host__ __device__ constexpr size_t up_smem_bytes(int D, int KS, int stages) {
-    // stages of D planes + tables + raw ring (UP_RAW skewed slots) + 1 KB slack + barriers
+    // stages of D planes + tables + raw ring (UP_RAW slots) + 1 KB slack + barriers
     return (size_t)stages * D * 2 * up_nsub(KS) + UP_RAW * up_raw_bytes(D, KS) + (size_t)D * KS * 48 * 32 + 1024 + 256;
 }
 
-// roles: 8 producer warps (the phase split is the heavy part here), 2 MMA warps taking alternate tiles (a small-N
-// tcgen05.mma costs its issuing thread ~45-80 cycles: one issuer left the tensor pipe 80 % idle), 8 epilogue warps
-constexpr int UP_PROD_WARPS = 8, UP_MMA_WARP = UP_PROD_WARPS, UP_MMA_WARPS = 2, UP_EPI_WARP0 = UP_PROD_WARPS + UP_MMA_WARPS,
-              UP_THREADS = (UP_PROD_WARPS + UP_MMA_WARPS + 8) * 32;
+// roles: 9 converter warps (the phase split; 268 half units per tile at D = 10), 1 loader warp, 2 MMA warps taking
+// alternate tiles, 8 epilogue warps (warp % 4 = TMEM lane quarter)
+constexpr int UP_CONV_WARPS = 9, UP_LOAD_WARP = UP_CONV_WARPS, UP_MMA_WARP = UP_CONV_WARPS + 1, UP_MMA_WARPS = 2,
+              UP_EPI_WARP0 = UP_MMA_WARP + UP_MMA_WARPS, UP_THREADS = (UP_EPI_WARP0 + 8) * 32;
+static_assert(UP_EPI_WARP0 % 4 == 0, "epilogue warps must start on a TMEM lane-quarter boundary");
 
-template <int D, int RM>
+// all D * KS MMAs of a tile, fully unrolled: A descriptor = plane p (PLB / 16 = 128 + 2 KS descriptor units apart) + 2 kk,
+// B descriptor = block p * KS + kk of the table (48 x 32 B = 96 units)
+template <int D, int KS>
+__device__ __forceinline__ void up_issue_tile(uint32_t d0, uint64_t ap, uint64_t bd, uint32_t idesc) {
+    constexpr uint64_t PSTEP = 128 + 2 * KS, BSTEP = (48 * 32) >> 4;
+    umma_i8c<false>(d0, ap, bd, idesc);
+#pragma unroll
+    for (int j = 1; j < D * KS; ++j)
+        umma_i8c<true>(d0, ap + (uint64_t)(j / KS) * PSTEP + 2 * (uint64_t)(j % KS), bd + (uint64_t)j * BSTEP, idesc);
+}
+
+template <int D>
 __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmArgs a) {
     constexpr int N = 48;
-    // converting producer lanes: in the bulk-copy modes the last producer warp only loads
-    constexpr int NCONV = 32 * (RM ? UP_PROD_WARPS - 1 : UP_PROD_WARPS);
+    constexpr int NCONV = 32 * UP_CONV_WARPS;
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * UM_STAGES + 2 * UP_SETS + 2 * UP_RAW + 1];
     __shared__ uint32_t tmem_base_s;
@@ -858,15 +866,10 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
     auto rawfull_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + 2 * UP_SETS + s); };
     auto rawfree_bar = [&](int s) { return bar0 + 8u * (2 * UM_STAGES + 2 * UP_SETS + UP_RAW + s); };
     const uint32_t tab_bar = bar0 + 8u * (2 * UM_STAGES + 2 * UP_SETS + 2 * UP_RAW);
-    if (RM == 0) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(a.tab);
-        uint4 *dst = reinterpret_cast<uint4 *>(gen + NST * SB);
-        for (int i = tid; i < D * KS * N * 2; i += UP_THREADS) dst[i] = __ldg(src + i);
-    }
     if (tid == 0) {
         for (int s = 0; s < UM_STAGES; ++s) { mbar_init(full_bar(s), NCONV); mbar_init(empty_bar(s), 1); }
         for (int s = 0; s < UP_SETS; ++s) { mbar_init(accf_bar(s), 1); mbar_init(acce_bar(s), 4); }
-        for (int s = 0; s < UP_RAW; ++s) { mbar_init(rawfull_bar(s), 1); mbar_init(rawfree_bar(s), UP_PROD_WARPS - 1); }
+        for (int s = 0; s < UP_RAW; ++s) { mbar_init(rawfull_bar(s), 1); mbar_init(rawfree_bar(s), UP_CONV_WARPS); }
         mbar_init(tab_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -882,9 +885,9 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
     const long long nwork = (long long)a.ntiles * f.n_ch;
     const long long wstride = gridDim.x;
 
-    if (RM != 0 && warp == UP_PROD_WARPS - 1) {
-        // ================= loader warp (bulk-copy modes): raw tiles by TMA bulk copies, UP_RAW tiles ahead =================
-        // The legacy mode gives every lane ITS unit's 16 D contiguous bytes as D 16-byte cp.async: a warp instruction then
+    if (warp == UP_LOAD_WARP) {
+        // ================= loader warp: raw tiles by TMA bulk copies, UP_RAW tiles ahead =================
+        // Round 1 gave every lane ITS unit's 16 D contiguous bytes as D 16-byte cp.async: a warp instruction then
         // touches 32 different 128-byte lines (lane stride 16 D bytes), i.e. 32 L1 tag passes for 512 bytes.  Here the
         // copy engine moves the tile: ONE bulk copy into a linear slot.  (One copy per skew group of 8 / gcd(D, 8) units,
         // which keeps the conflict-free skewed layout, was measured far slower: 34 copies of 640 bytes per tile.)
@@ -938,10 +941,13 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
                 }
             }
         }
-    } else if (RM != 0 && warp < UP_PROD_WARPS) {
-        // ================= converters (bulk-copy modes): raw slot -> D phase planes =================
+    } else if (warp < UP_CONV_WARPS) {
+        // ================= converters: raw slot -> D phase planes =================
         const int ptid = warp * 32 + lane;
-        const int nunits = NSUB / 8;
+        constexpr bool HALF = up_half(D);
+        constexpr int CH = HALF ? D / 2 : D;    // 16-byte chunks per item
+        constexpr int NW = HALF ? 2 : 4;        // output words per plane per item
+        const int nitems = (NSUB / 8) * (HALF ? 2 : 1);
         const int RAWB = (int)up_raw_bytes(D, KS);
         int stage = 0, slot = 0;
         uint32_t ph = 0, rph = 0;
@@ -950,132 +956,42 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
             mbar_wait(empty_bar(stage), ph ^ 1u);
             uint8_t *st_g = gen + (size_t)stage * SB;
             const uint8_t *rs = raw0 + (size_t)slot * RAWB;
-            for (int v = ptid; v < nunits; v += NCONV) {
-                uint32_t rw[4 * D];
-                const int sk = 0;  // linear slot
+            for (int i = ptid; i < nitems; i += NCONV) {
+                uint32_t rw[4 * CH];  // the item's samples, 2 per word (I, Q bytes of a sample stay together)
 #pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(rs + 16 * (v * D + sk + c));
+                for (int c = 0; c < CH; ++c) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(rs + 16 * (i * CH + c));
                     rw[4 * c] = q.x; rw[4 * c + 1] = q.y; rw[4 * c + 2] = q.z; rw[4 * c + 3] = q.w;
                 }
 #pragma unroll
                 for (int p = 0; p < D; ++p) {
-                    uint32_t o[4];
+                    uint32_t o[NW];
 #pragma unroll
-                    for (int wd = 0; wd < 4; ++wd) {
+                    for (int wd = 0; wd < NW; ++wd) {
+                        // plane sub-samples 2wd, 2wd+1 of this item = its raw samples D*(2wd) + p, D*(2wd+1) + p
+                        // (an item starts an even number of samples into its unit: the parities are the unit's)
                         const int sa = D * (2 * wd) + p, sb = D * (2 * wd + 1) + p;
                         const uint32_t sel = (uint32_t)(2 * (sa & 1)) | ((uint32_t)(2 * (sa & 1) + 1) << 4) |
                                              ((uint32_t)(4 + 2 * (sb & 1)) << 8) | ((uint32_t)(5 + 2 * (sb & 1)) << 12);
                         o[wd] = __byte_perm(rw[sa >> 1], rw[sb >> 1], sel);
                     }
-                    *reinterpret_cast<uint4 *>(st_g + (size_t)p * PLB + 16 * v) = make_uint4(o[0], o[1], o[2], o[3]);
+                    if (HALF) *reinterpret_cast<uint2 *>(st_g + (size_t)p * PLB + 8 * i) = make_uint2(o[0], o[1]);
+                    else *reinterpret_cast<uint4 *>(st_g + (size_t)p * PLB + 16 * i) = make_uint4(o[0], o[1], o[NW - 2], o[NW - 1]);
                 }
             }
-            fence_proxy_async();
+            fence_proxy_async();  // plain stores -> visible to the tensor core's (async proxy) operand reads
             mbar_arrive(full_bar(stage));
             __syncwarp();
             if (lane == 0) mbar_arrive(rawfree_bar(slot));  // this warp's reads of the slot are done
             if (++stage == NST) { stage = 0; ph ^= 1u; }
             if (++slot == UP_RAW) { slot = 0; rph ^= 1u; }
         }
-    } else if (RM == 0 && warp < UP_PROD_WARPS) {
-        // ================= producers: raw ring (cp.async, two tiles ahead) -> D phase planes =================
-        const int ptid = warp * 32 + lane;
-        const int nunits = NSUB / 8;  // a unit = 8 sub-samples of every phase = D raw chunks = D plane chunks
-        const int RAWB = (int)up_raw_bytes(D, KS);
-        auto issue = [&](long long w, int slot) {
-            if (w < nwork) {
-                int ch; long long wt;
-                split_work(w, a.ntiles, (int)f.n_ch, ch, wt);
-                // first raw sample of the tile; A0 = first - (K-1) - delta is a multiple of 8
-                const long long w0 = f.first - (f.K - 1) - a.delta + wt * (long long)(UP_TILE_OUT * D);
-                const unsigned char *in = (const unsigned char *)f.in + (long long)ch * f.in_stride * 2;
-                const unsigned char *hist = (const unsigned char *)f.hist + (long long)ch * f.hist_stride * 2;
-                uint8_t *rs = raw0 + (size_t)slot * RAWB;
-                const uint32_t rs_s = smem_u32(rs);
-                const bool interior = w0 >= 0 && w0 + 8LL * nunits * D <= f.n_in;
-                if (interior) {
-                    // the common case, kept free of the boundary code: a lane's D chunks are 16 D contiguous bytes
-                    for (int v = ptid; v < nunits; v += 32 * UP_PROD_WARPS) {
-                        const unsigned char *src = in + 2 * (w0 + 8LL * v * D);
-                        const uint32_t dst = rs_s + 16u * (uint32_t)(v * D + up_skew(D, v));
-#pragma unroll
-                        for (int c = 0; c < D; ++c) cp_async16_s(dst + 16u * c, src + 16 * c);
-                    }
-                } else
-                for (int v = ptid; v < nunits; v += 32 * UP_PROD_WARPS) {
-#pragma unroll 1
-                    for (int c = 0; c < D; ++c) {
-                        const int q = v * D + c;
-                        const long long s0 = w0 + 8LL * q;
-                        const int qs = q + up_skew(D, v);  // skewed slot of the chunk
-                        if (s0 >= 0 && s0 + 8 <= f.n_in) {
-                            cp_async16_s(rs_s + 16u * qs, in + 2 * s0);
-                        } else if (s0 < f.n_in) {
-                            unsigned short h[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const long long s = s0 + i;
-                                unsigned short x = 0x8080;
-                                if (s >= 0) { if (s < f.n_in) x = *reinterpret_cast<const unsigned short *>(in + 2 * s); }
-                                else if (s >= -(long long)f.HL) x = *reinterpret_cast<const unsigned short *>(hist + 2 * ((long long)f.HL + s));
-                                h[i] = x;
-                            }
-                            uint4 qv;
-                            qv.x = h[0] | ((unsigned)h[1] << 16); qv.y = h[2] | ((unsigned)h[3] << 16);
-                            qv.z = h[4] | ((unsigned)h[5] << 16); qv.w = h[6] | ((unsigned)h[7] << 16);
-                            *reinterpret_cast<uint4 *>(rs + 16 * qs) = qv;  // read back by this same lane
-                        }
-                    }
-                }
-            }
-            asm volatile("cp.async.commit_group;" ::: "memory");
-        };
-#pragma unroll
-        for (int i = 0; i < UP_RAW - 1; ++i) issue(blockIdx.x + i * wstride, i);
-        int stage = 0, slot = 0;
-        uint32_t ph = 0;
-        for (long long w = blockIdx.x; w < nwork; w += wstride) {
-            int s2 = slot + UP_RAW - 1;
-            if (s2 >= UP_RAW) s2 -= UP_RAW;
-            issue(w + (UP_RAW - 1) * wstride, s2);
-            asm volatile("cp.async.wait_group %0;" ::"n"(UP_RAW - 1) : "memory");  // this lane's chunks of tile w have landed
-            mbar_wait(empty_bar(stage), ph ^ 1u);
-            uint8_t *st_g = gen + (size_t)stage * SB;
-            const uint8_t *rs = raw0 + (size_t)slot * RAWB;
-            for (int v = ptid; v < nunits; v += 32 * UP_PROD_WARPS) {
-                uint32_t rw[4 * D];  // the unit's 8 D samples, 2 per word (I, Q bytes of a sample stay together)
-#pragma unroll
-                for (int c = 0; c < D; ++c) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(rs + 16 * (v * D + up_skew(D, v) + c));
-                    rw[4 * c] = q.x; rw[4 * c + 1] = q.y; rw[4 * c + 2] = q.z; rw[4 * c + 3] = q.w;
-                }
-#pragma unroll
-                for (int p = 0; p < D; ++p) {
-                    uint32_t o[4];
-#pragma unroll
-                    for (int wd = 0; wd < 4; ++wd) {
-                        // plane sub-samples 2wd, 2wd+1 of this unit = raw samples D*(2wd) + p, D*(2wd+1) + p
-                        const int sa = D * (2 * wd) + p, sb = D * (2 * wd + 1) + p;
-                        const uint32_t sel = (uint32_t)(2 * (sa & 1)) | ((uint32_t)(2 * (sa & 1) + 1) << 4) |
-                                             ((uint32_t)(4 + 2 * (sb & 1)) << 8) | ((uint32_t)(5 + 2 * (sb & 1)) << 12);
-                        o[wd] = __byte_perm(rw[sa >> 1], rw[sb >> 1], sel);
-                    }
-                    *reinterpret_cast<uint4 *>(st_g + (size_t)p * PLB + 16 * v) = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-            }
-            fence_proxy_async();  // plain stores -> visible to the tensor core's (async proxy) operand reads
-            mbar_arrive(full_bar(stage));
-            if (++stage == NST) { stage = 0; ph ^= 1u; }
-            if (++slot == UP_RAW) slot = 0;
-        }
-        asm volatile("cp.async.wait_all;" ::: "memory");
     } else if (warp < UP_EPI_WARP0) {
         // ================= MMA issuers: warp j takes tiles j, j + 2, ...; D phases x KS k-steps into one set =================
         const int mw = warp - UP_MMA_WARP;
         const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((128u >> 4) << 24);
         const uint64_t bdesc0 = smem_desc(tab_s, 128, 256, 0);
-        if (RM != 0) {
+        {
             // the tap tables arrive by one bulk copy while the first raw tile is loaded and converted
             if (mw == 0 && elect_one()) {
                 mbar_arrive_expect_tx(tab_bar, (uint32_t)(D * KS * N * 32));
@@ -1093,23 +1009,20 @@ __global__ void __launch_bounds__(UP_THREADS, 1) fir_umma_poly_kernel(const UmAr
             mbar_wait(acce_bar(as), aph ^ 1u);
             tc_fence_after();
             if (elect_one()) {
-                // running descriptors (two 64-bit adds of constants per MMA on the uniform datapath)
-                uint64_t ap = smem_desc(stage0 + (uint32_t)stage * SB, 16, 128, 0);  // plane 0
-                uint64_t bd = bdesc0;
+                const uint64_t ap = smem_desc(stage0 + (uint32_t)stage * SB, 16, 128, 0);  // plane 0
                 const uint32_t d0 = tmem + (uint32_t)(as * N);
-                const uint64_t pstep = (uint64_t)(PLB >> 4);
-                umma_i8c<false>(d0, ap, bd, idesc);
-                for (int kk = 1; kk < KS; ++kk) {
-                    bd += (N * 32) >> 4;
-                    umma_i8c<true>(d0, ap + 2 * kk, bd, idesc);
-                }
-#pragma unroll 1
-                for (int p = 1; p < D; ++p) {
-                    ap += pstep;
-                    for (int kk = 0; kk < KS; ++kk) {
-                        bd += (N * 32) >> 4;
-                        umma_i8c<true>(d0, ap + 2 * kk, bd, idesc);
-                    }
+                // KS is a run-time value; a loop over it made ptxas emit a dependent chain of ~12 uniform-datapath
+                // instructions per MMA (ncu: the two issuing warps were busy 86 % of the time, ~145 cycles per MMA, with
+                // the tensor pipe 40 % active).  Dispatch to straight-line code per KS instead: every descriptor is the
+                // tile's base plus an immediate.
+                switch (KS) {
+                    case 1: up_issue_tile<D, 1>(d0, ap, bdesc0, idesc); break;
+                    case 2: up_issue_tile<D, 2>(d0, ap, bdesc0, idesc); break;
+                    case 3: up_issue_tile<D, 3>(d0, ap, bdesc0, idesc); break;
+                    case 4: up_issue_tile<D, 4>(d0, ap, bdesc0, idesc); break;
+                    case 5: up_issue_tile<D, 5>(d0, ap, bdesc0, idesc); break;
+                    case 6: up_issue_tile<D, 6>(d0, ap, bdesc0, idesc); break;
+                    default: up_issue_tile<D, 7>(d0, ap, bdesc0, idesc); break;
                 }
                 umma_commit(empty_bar(stage));
                 umma_commit(accf_bar(as));
@@ -1365,22 +1278,15 @@ static int fir_umma_poly_launch(const FirArgs &f, const uint8_t *d_tables, const
         count_launch();
         return launch_status();
     };
-    // raw-tile staging: 0 = per-lane cp.async (round 1), 1 = one TMA bulk copy per tile
-    static const int rm_env = []() { const char *e = std::getenv("SDR_UP_RAW"); return e ? std::atoi(e) : UP_RAW_MODE_DEFAULT; }();
-#define SDR_UP_CASE(DD)                                              \
-    case DD:                                                         \
-        if (rm_env == 0) return go(fir_umma_poly_kernel<DD, 0>);     \
-        return go(fir_umma_poly_kernel<DD, 1>);
     switch (D) {
-        SDR_UP_CASE(5)
-        SDR_UP_CASE(6)
-        SDR_UP_CASE(7)
-        SDR_UP_CASE(8)
-        SDR_UP_CASE(9)
-        SDR_UP_CASE(10)
-        SDR_UP_CASE(12)
+        case 5: return go(fir_umma_poly_kernel<5>);
+        case 6: return go(fir_umma_poly_kernel<6>);
+        case 7: return go(fir_umma_poly_kernel<7>);
+        case 8: return go(fir_umma_poly_kernel<8>);
+        case 9: return go(fir_umma_poly_kernel<9>);
+        case 10: return go(fir_umma_poly_kernel<10>);
+        case 12: return go(fir_umma_poly_kernel<12>);
     }
-#undef SDR_UP_CASE
     return SDR_ERR_UNSUPPORTED;
 }
 
