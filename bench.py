@@ -338,8 +338,10 @@ class Ctx:
         self.barrier()
         l0 = self.sdr.kernel_launch_count()
         ev0.record()
+        t0 = time.perf_counter()
         for _ in range(steps):
             step()
+        self.host_ms_per_step = (time.perf_counter() - t0) * 1e3 / steps  # enqueue time only (nothing synchronises in a step)
         ev1.record()
         self.barrier()
         launches = self.sdr.kernel_launch_count() - l0
@@ -642,7 +644,8 @@ def measure_config(cx, name, steps, warmup, peak):
     entry = {"workload": cfg["workload"], "desc": cfg["desc"], "value": units_all / (ms * 1e-3) / 1e9,
              "unit": "Gsamples/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
              "samples_per_step_all_gpus": units_all, "sharding": wl.get("sharding"), "parity_bit_exact": parity,
-             "gpu_launches": launches, "dtype": wl["dtype"], "kernel": wl["kernel"],
+             "gpu_launches": launches, "host_enqueue_ms_per_step": round(cx.host_ms_per_step, 4),
+             "dtype": wl["dtype"], "kernel": wl["kernel"],
              "roofline": {"bound": wl.get("bound", "hbm"), "achieved": achieved, "peak": peak, "unit": "GB/s",
                           "frac": achieved / peak, "algorithmic_bytes_per_sample": wl["bytes_per_unit"],
                           "traffic": NCU_TRAFFIC.get(cfg["workload"], (None, None))[0]},
@@ -816,7 +819,8 @@ def main():
                          "algorithmic_bytes": wl["units"] * wl["bytes_per_unit"],
                          "peak_source": peak_src, "kernel": wl["kernel"],
                          "algorithmic_bytes_per_sample": wl["bytes_per_unit"]},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clk.summary(),
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": round(cx.host_ms_per_step, 4), "clocks": clk.summary(),
             "configs": configs,
         }
         print(json.dumps(line), flush=True)

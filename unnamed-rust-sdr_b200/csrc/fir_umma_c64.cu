@@ -273,24 +273,17 @@ __global__ void __launch_bounds__(UC_THREADS, 1) fir_umma_c64_kernel(const UcArg
                 split(w, ch, wt);
                 const long long j0 = f.in_step * tile_s0(wt) + f.in_off - ch;
                 const float2 *in = (const float2 *)f.in;
-                // all of a lane's loads of a batch are issued before the first store: one round trip to L2 per batch of 10
-                // (the loop was unrolled by 4 with the store behind each load: ~5 dependent round trips per tile, ncu: the
-                // producers spent 55 % of their time on that store)
-                for (int e0 = ptid; e0 < NEL; e0 += 10 * 32 * UC_PROD_WARPS) {
-                    float2 v[10];
-#pragma unroll
-                    for (int k = 0; k < 10; ++k) {
-                        const int e = e0 + k * 32 * UC_PROD_WARPS;
-                        const long long j = j0 + f.in_step * e;
-                        v[k] = make_float2(0.0f, 0.0f);
-                        if (e < NEL && j >= 0 && j < f.in_limit) v[k] = __ldg(in + j);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 10; ++k) {
-                        const int e = e0 + k * 32 * UC_PROD_WARPS;
-                        if (e < NEL) *reinterpret_cast<float2 *>(rs + 8 * e) = v[k];
-                    }
+                // 8-byte cp.async with zero fill: all of a lane's ~18 copies are in flight at once and nothing passes through
+                // registers (first version: LDG + STS unrolled by 4, ~5 dependent round trips to L2 per tile -- ncu: the
+                // producers spent 55 % of their time there; batches of 10 loads: 2 round trips)
+                const uint32_t rs_s = raw_s + (uint32_t)slot * RAWB;
+                for (int e = ptid; e < NEL; e += 32 * UC_PROD_WARPS) {
+                    const long long j = j0 + f.in_step * e;
+                    const bool ok = j >= 0 && j < f.in_limit;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(rs_s + 8u * (uint32_t)e), "l"(ok ? in + j : in), "r"(ok ? 8 : 0) : "memory");
                 }
+                asm volatile("cp.async.commit_group;" ::: "memory");
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
                 prod_bar_sync();
             } else if (e_hi - e_lo < NEL) {
                 int ch; long long wt;
