@@ -422,7 +422,7 @@ __device__ __forceinline__ void reg2_middle(float2 *sx, const float2 *tab, int t
     group_sync<TC>(group);
 }
 
-// REGPF (n = 8192, c64): the next transform's pass-0 inputs are prefetched into REGISTERS (16 LDG.64 per thread, issued
+// REGPF (n = 2048 .. 8192, c64): the next transform's pass-0 inputs are prefetched into REGISTERS (16 LDG.64 per thread, issued
 // behind pass 0, consumed one transform later) instead of a cp.async raw copy in shared memory: the raw copy cost 128 KB
 // of the 512 KB of shared-memory traffic per transform in a kernel whose phases are serialised by CTA-wide barriers.
 template <int LOGN, int FMT, bool REGPF = false>
@@ -551,8 +551,11 @@ template <int LOGN, int FMT>
 int launch_reg2(const FftArgs &a, cudaStream_t st) {
     using PL = Reg2Plan<LOGN>;
     static const int mode8k = std::getenv("SDR_FFT8K") ? std::atoi(std::getenv("SDR_FFT8K")) : 1;  // A/B switch: 0 = cp.async raw copy
-    constexpr bool CAN_REGPF = PL::PREFETCH && FMT == SDR_FMT_C64;
-    const bool regpf = CAN_REGPF && mode8k == 1;
+    // register prefetch below 8192: measured on one box (profiles/r02_ab_fft_regpf.txt) +7-9 % at 2048 and 4096 (two CTAs
+    // per SM, 117-122 registers), -4 % / -9 % at 256 / 512.  A/B switch SDR_FFT_REGPF_MIN = smallest log2 n that uses it.
+    static const int regpf_min = std::getenv("SDR_FFT_REGPF_MIN") ? std::atoi(std::getenv("SDR_FFT_REGPF_MIN")) : 11;
+    constexpr bool CAN_REGPF = (PL::PREFETCH || LOGN >= 11) && FMT == SDR_FMT_C64;
+    const bool regpf = CAN_REGPF && (PL::PREFETCH ? mode8k == 1 : LOGN >= regpf_min);
     const size_t smem = regpf ? PL::raw_offset() : PL::smem_bytes(FmtBytes<FMT>::v);
     if (!regpf && PL::PREFETCH && (((uintptr_t)a.in) & 15)) return launch_cta<LOGN, FMT>(a, st);  // cp.async needs 16-byte rows
     void (*kern)(FftArgs) = fft_reg2_kernel<LOGN, FMT, false>;
