@@ -790,27 +790,29 @@ __global__ void __launch_bounds__(UM_THREADS, 1) fir_umma_planar_kernel(const Um
 
 // =====================================================================================================================
 // Polyphase variant for Decimate with D >= 5 (config C3: 255 taps, D = 10).  The candidate-offset kernel above spends
-// its MMAs on all 32/g offsets of a row although only one in D/g is a kept output.  Here the producers split the stream
-// into D PHASE PLANES x_p[n] = x[A0 + D n + p] (a lane takes 8 n x D phases = D raw 16-byte chunks and emits one
-// 16-byte chunk per plane: one PRMT per output word), and
+// its MMAs on all 32/g offsets of a row although only one in D/g is a kept output.  Here the stream is split
+// into D PHASE PLANES x_p[n] = x[A0 + D n + p] (a converter lane takes 4 or 8 n x D phases = whole raw 16-byte chunks and
+// emits one 8- or 16-byte piece per plane: one PRMT per output word), and
 //     y[m] = sum_p sum_t h_p[t] x_p[m + t],      h_p[t] = c[K-1 - (D t + p - delta)]
 // is D short unit-stride FIRs: per phase a Toeplitz MMA chain with rows 8 outputs apart (16-byte pitch, no swizzle,
 // N = 48), all accumulating into the same TMEM columns, and EVERY computed output is kept.  MMA operand traffic per
 // input sample drops from 33 to 16 bytes, the kept-output test disappears from the epilogue.
 // =====================================================================================================================
-// MEASURED AND REMOVED (round 2): the same kernel with window rows 16 outputs apart (32-byte pitch = SWIZZLE_32B, N = 96: the
-// same 30 MMAs produce 2048 outputs instead of 1024 -- half the tensor time per output, half the hand-overs), tables doubled,
-// the raw ring dropped for room (producers LDG.128 their unit one tile ahead into registers).  Correct (bit-identical
-// integer sums, the whole FIR suite passed) and NOT faster: 930 vs 1035 Gsamples/s at 2^26 samples (22 tiles per SM: ramp and
-// tail weigh more with larger tiles), 1142 vs 1160 at 2^28 -- both kernels saturate at ~0.49 of the roofline there, so the MMA
-// count is not what bounds C3.  ncu: the producers wait for their own loads (15 % of all stall samples on the first PRMT
-// behind the LDGs): one tile of loads in flight per SM (42 KB / ~2.6 us) is what Little's law gives for the observed
-// 2.3 TB/s of reads.  A second register set (two tiles ahead) spilled at the 104-register budget of 608 threads and was
-// slower still (749); an L2 prefetch two tiles ahead changed nothing.  What this kernel family needs for C3 is more bytes
-// in flight per SM, i.e. a deeper raw ring, which the 92 KB of N = 96 tables leave no shared memory for.
+// Staging (round 2): a loader warp brings every raw tile by ONE TMA bulk copy into a ring of linear slots, converter warps
+// split a slot into the planes.  (Round 1: every producer lane cp.async'ed ITS unit's 16 D contiguous bytes so that no
+// barrier was needed between the copy and the split -- a warp instruction then touched 32 different 128-byte lines, and
+// that, not the MMA count, was what C3 saturated on: 1036 -> 1500 Gsamples/s, profiles/r02_ab_c3_poly.txt.)
+// MEASURED AND REMOVED (round 2, each bit-identical and green on the whole FIR suite, each within 5 % of this kernel on the
+// same box): window rows 16 outputs apart (32-byte pitch = SWIZZLE_32B, N = 96: the same 30 MMAs produce 2048 outputs, 36 %
+// less tensor operand traffic, but 92 KB of tables leave room for two half-tile raw slots only: -5 .. -9 %; an earlier
+// version without any raw ring: 930 vs 1035); I / Q byte planes (16 outputs per 16-byte row, 40 MMAs of N = 48 per 2048
+// outputs, a third less operand traffic, 40 instead of 20 PRMT per converter item: equal at 2^28, -3 % at 2^26); skipping
+// the last k-step of phases whose taps end earlier (27 instead of 30 MMAs: -2 %).  ncu of THIS kernel: the tensor core's
+// shared-memory operand pipe is 91 % busy (44 wavefronts per MMA = 32 of A + 12 of B); with it relieved, the converters or
+// the raw ring take over at the same level.
 constexpr int UP_TILE_OUT = 1024;  // outputs per tile = 128 rows x 8
 constexpr int UP_SETS = 4;         // accumulator sets of 48 TMEM columns
-constexpr int UP_RAW = 3;          // raw ring slots: cp.async runs 2 tiles ahead (deeper rings measured no better)
+constexpr int UP_RAW = 3;          // raw ring slots: the loader runs up to 3 tiles ahead (21 KB bulk copies reach the full HBM rate from 3 slots on)
 __host__ __device__ constexpr int up_ksteps(int K, int D) { return (7 + (K + 6) / D) / 16 + 1; }
 __host__ __device__ constexpr int up_nsub(int KS) { return 8 * 128 + 16 * KS; }  // sub-samples per plane per tile
 // Raw slots are LINEAR copies of the input (one TMA bulk copy each).  A converter lane reads whole 16-byte chunks of its
