@@ -834,6 +834,9 @@ extern "C" sdr_pll_t *sdr_pll_create(const sdr_pll_config_t *cfg, int *err) {
         q.rate = cfg->rate;
         q.lk = d.loopfilter.kind; q.ok = d.outputfilter.kind; q.kk = d.lockfilter.kind;
         if (q.lk == SDR_BQ_IDENTITY || q.ok == SDR_BQ_IDENTITY || q.kk == SDR_BQ_IDENTITY) p->any_identity = true;
+        // the specialised kernel also assumes |nphase + reference + gain * arg| < 2 (nphase in (-1, 1), |arg| <= pi), so
+        // that f32::fract needs no general trunc; designs with a larger step per sample take the general kernel
+        if (!(std::fabs(q.reference) + 3.1416f * std::fabs(q.gain) < 0.999f)) p->any_identity = true;
         int rc = sdr_biquad_design(&d.loopfilter, cfg->rate, q.lc);
         if (!rc) rc = sdr_biquad_design(&d.outputfilter, cfg->rate, q.oc);
         if (!rc) rc = sdr_biquad_design(&d.lockfilter, cfg->rate, q.kc);

@@ -203,6 +203,70 @@ __device__ __forceinline__ void sincos_t(float xf, T &sn, T &cs) {
     cs = ((q + 1) & 2) ? -b : b;
 }
 
+// ---- f32 routines arranged for DEPTH (round 2) -------------------------------------------------------------------
+// The recurrence is one dependent chain per stream, so only the depth of these counts.  Both are accurate to ~1 ulp
+// (the oracle calls glibc's atan2f / sinf / cosf, themselves within an ulp); tests/test_gpu_pll_resample.py holds the
+// resulting trajectories to the same bars as the f64 routines above (measured: max 3.2e-6 / median 2.0e-7 of full
+// scale against 3.6e-6 / 1.4e-7 -- a last-bit difference in arg or in the NCO is far below one ulp of the f32 phase
+// accumulator it is added to).
+//   atan2: |y|, |x| ordered by two FMNMX; BOTH quotients mn / mx and (mn - mx) / (mn + mx) (the tan(pi/8) reduction) are
+//          formed -- MUFU.RCP + one Newton step each -- so that the select between them waits for nothing; atan(t) =
+//          t + t z A(z), z = t^2 <= tan^2(pi/8), A of degree 4 (near-minimax, relative error 2.8e-9), Estrin in 3 levels;
+//          the octant fix-ups are one fma(S, r, C), S = +-1 and C from the operand signs, off the chain.
+//   sincos: k = rint(x * 2/pi) by the 1.5 * 2^23 magic number (no FRND / F2I on the chain), two-constant Cody-Waite,
+//          degree-3 near-minimax polynomials in s = r^2 for (sin r / r - 1) / s and (cos r - 1) / s (errors 7e-11,
+//          3.4e-10), Estrin in 2 levels, quadrant from the low bits of the biased float, sign by XOR.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float div_nr(float num, float den) {  // den in [2^-100, 2^100]: seed + one Newton step
+    const float r0 = rcp_approx(den);
+    const float q0 = num * r0;
+    return __fmaf_rn(__fmaf_rn(-den, q0, num), r0, q0);
+}
+__device__ __forceinline__ float atan2_fast(float yf, float xf) {
+    const float axf = fabsf(xf), ayf = fabsf(yf);
+    const float mx = fmaxf(axf, ayf), mn = fminf(axf, ayf);
+    const bool red = mn > 0.41421357f * mx;
+    const bool swap = ayf > axf, xneg = __float_as_int(xf) < 0, yneg = __float_as_int(yf) < 0;
+    float C = red ? 0.78539816339744831f : 0.0f, S = 1.0f;
+    if (swap) { C = 1.5707963267948966f - C; S = -S; }
+    if (xneg) { C = 3.1415926535897932f - C; S = -S; }
+    if (yneg) { C = -C; S = -S; }
+    // ONE division behind the select (the main warp is issue bound at ~2 cycles per instruction: a second speculative
+    // quotient costs more than the select's latency).  No range branch: the divisor is clamped from below (0 / 0 -> 0, as
+    // atan2(+-0, +-0) needs); magnitudes beyond 2^126, where rcp.approx.ftz flushes to zero, are not supported by this
+    // routine (the products of pll.rs:71 overflow there anyway), NaN propagates as it does in the reference.
+    const float num = red ? mn - mx : mn;
+    const float den = fmaxf(red ? mn + mx : mx, 1e-37f);
+    const float t = div_nr(num, den);
+    const float z = t * t, z2 = z * z, tz = t * z;
+    const float p0 = __fmaf_rn(0.199996680021286f, z, -0.3333333432674408f);
+    const float p1 = __fmaf_rn(0.10767315328121185f, z, -0.14266839623451233f);
+    const float q = __fmaf_rn(-0.06515224277973175f, z2, p1);
+    const float A = __fmaf_rn(q, z2, p0);
+    const float r = __fmaf_rn(tz, A, t);
+    return __fmaf_rn(S, r, C);
+}
+__device__ __forceinline__ void sincos_fast(float xf, float &sn, float &cs) {
+    const float kb = __fmaf_rn(xf, 0.63661977236758134f, 12582912.0f);
+    const float kf = kb - 12582912.0f;
+    const int q = __float_as_int(kb);  // low two bits = k mod 4
+    float r = __fmaf_rn(-kf, 1.57079637050628662109375f, xf);
+    r = __fmaf_rn(-kf, -4.37113882867379e-8f, r);
+    const float s = r * r, s2 = s * s, rs = r * s;
+    const float ps = __fmaf_rn(__fmaf_rn(2.7417770525062224e-06f, s, -0.00019841655739583075f), s2,
+                               __fmaf_rn(0.008333335630595684f, s, -0.1666666716337204f));
+    const float pc = __fmaf_rn(__fmaf_rn(2.4507638954673894e-05f, s, -0.0013888041721656919f), s2,
+                               __fmaf_rn(0.0416666641831398f, s, -0.5f));
+    const float sr = __fmaf_rn(rs, ps, r), cr = __fmaf_rn(s, pc, 1.0f);
+    const float a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
+    sn = __int_as_float(__float_as_int(a) ^ ((q & 2) << 30));
+    cs = __int_as_float(__float_as_int(b) ^ (((q + 1) & 2) << 30));
+}
+
 // The recurrence (pll.rs:71-76): everything the NEXT sample depends on.  Returns c.re and phasedif for the two filters
 // that do not feed back (lock, output), which a helper warp applies one tile later.
 template <bool FAST, bool GEN>
@@ -215,17 +279,32 @@ __device__ __forceinline__ float2 pll_step(const PllParams &p, const Biquad1 &lf
     const float lr = bq_apply<GEN>(lf, cr, s.lx1r, s.lx2r, s.ly1r, s.ly2r);
     const float li = bq_apply<GEN>(lf, ci, s.lx1i, s.lx2i, s.ly1i, s.ly2i);
     // phasedif = arg * gain                   (pll.rs:72)
-    const float arg = FAST ? atan2_t<float>(li, lr) : (float)atan2_t<double>(li, lr);
+    const float arg = FAST ? atan2_fast(li, lr) : (float)atan2_t<double>(li, lr);
     const float phasedif = __fmul_rn(arg, p.gain);
     // nphase += reference + phasedif; nphase = nphase.fract()      (pll.rs:73-74)
     float nph = __fadd_rn(s.nphase, __fadd_rn(p.reference, phasedif));
-    nph = __fsub_rn(nph, truncf(nph));
+    float phase;
+    if (FAST) {
+        // fract = nph - trunc(nph): |nph| < 2 (checked per design on the host for the specialised kernel, per sample in
+        // the general one), so trunc is 1, -1 or a zero with nph's sign: two compares and two selects instead of
+        // FRND.TRUNC (14-21 cycles).  Same value.
+        float tr = nph >= 1.0f ? 1.0f : __int_as_float(__float_as_int(nph) & (int)0x80000000);
+        tr = nph <= -1.0f ? -1.0f : tr;
+        if (GEN && !(fabsf(nph) < 2.0f)) {
+            // (volatile: ptxas otherwise speculates the FRND above the branch)
+            asm volatile("cvt.rzi.f32.f32 %0, %1;" : "=f"(tr) : "f"(nph));
+        }
+        nph = __fsub_rn(nph, tr);
+        phase = __fmul_rn(2.0f * PI_F, nph);
+    } else {
+        nph = __fsub_rn(nph, truncf(nph));
+        // phase = 2.0 * PI * nphase; value = from_polar(1.0, phase)     (pll.rs:75-76)
+        phase = __fmul_rn(2.0f * PI_F, nph);
+    }
     s.nphase = nph;
-    // phase = 2.0 * PI * nphase; value = from_polar(1.0, phase)     (pll.rs:75-76)
-    const float phase = __fmul_rn(2.0f * PI_F, nph);
     if (FAST) {
         float sn, cs;
-        sincos_t<float>(phase, sn, cs);
+        sincos_fast(phase, sn, cs);
         s.vre = cs;
         s.vim = sn;
     } else {
@@ -299,11 +378,17 @@ __global__ void __launch_bounds__(64) pll_kernel(const float2 *__restrict__ in, 
         if (role == 0) {
             if (tile < ntiles && live) {
                 const int cnt = (int)min((long long)PLL_CHUNK, n - tile * PLL_CHUNK);
-                float2 xn = s_in[buf][lane][0];
+                // running pointers (the indexed form recomputed the shared addresses with 7 instructions per sample) and
+                // an unroll by 2 (the biquad state rotation becomes register renaming): the main warp is ISSUE bound, ncu
+                // shows ~2 cycles per instruction with the samples spread evenly over the loop body
+                const float2 *pin = &s_in[buf][lane][0];
+                float2 *pmid = &s_mid[buf][lane][0];
+                float2 xn = pin[0];
+#pragma unroll 2
                 for (int i = 0; i < cnt; ++i) {
                     const float2 x = xn;
-                    xn = s_in[buf][lane][min(i + 1, PLL_CHUNK - 1)];  // next sample's load leaves the dependent chain
-                    s_mid[buf][lane][i] = pll_step<FAST, GEN>(p, lf, st, x.x, x.y);
+                    xn = pin[i + 1];  // next sample's load leaves the dependent chain (the row has a pad element)
+                    pmid[i] = pll_step<FAST, GEN>(p, lf, st, x.x, x.y);
                 }
             }
         } else {
