@@ -519,7 +519,7 @@ def wl_fir_c64(cx, key, K=255, total_ch=1024, log2_n=16, flags=0):
                 kernel=kern, sharding="%d channels, %d per GPU (shard.unit_range)" % (total_ch, n_ch))
 
 
-def wl_channelizer(cx, key="c4", total_ch=128, log2_n=16, fast=False):
+def wl_channelizer(cx, key="c4", total_ch=128, log2_n=16, fast=True):
     """C4: total_ch channels split over the ranks (shard.unit_range), each channel = 255-tap FIR + PLL"""
     torch, sdr, dev = cx.torch, cx.sdr, cx.dev
     import gen
@@ -563,7 +563,7 @@ def wl_channelizer(cx, key="c4", total_ch=128, log2_n=16, fast=False):
                 sharding="%d channels, %d per GPU (shard.unit_range)" % (total_ch, n_ch))
 
 
-def wl_fm(cx, n_st=128, log2_n=18, fast=False):
+def wl_fm(cx, n_st=128, log2_n=18, fast=True):
     """the FM stereo receiver of src/main.rs:32-81 for a batch of stations, device resident."""
     torch, sdr, dev = cx.torch, cx.sdr, cx.dev
     n = 1 << log2_n
@@ -584,8 +584,8 @@ def wl_fm(cx, n_st=128, log2_n=18, fast=False):
 def make_workload(name, cx):
     if name == "fm":
         return wl_fm(cx)
-    if name == "fmfast":
-        return wl_fm(cx, fast=True)
+    if name == "fmf64":
+        return wl_fm(cx, fast=False)
     if name == "fm1024":
         return wl_fm(cx, n_st=1024, log2_n=16)
     if name in ("c2", "fft1024_u8", "default"):
@@ -610,8 +610,8 @@ def make_workload(name, cx):
         return wl_fir_u8(cx, "fir255_u8", 255, 1)
     if name == "c4":
         return wl_channelizer(cx, "c4", 128 * cx.world, 16)
-    if name == "c4fast":
-        return wl_channelizer(cx, "c4", 128 * cx.world, 16, fast=True)
+    if name == "c4f64":
+        return wl_channelizer(cx, "c4", 128 * cx.world, 16, fast=False)
     if name == "c4_1024":
         return wl_channelizer(cx, "c4_1024", 1024, 16)
     if name.startswith("c5_"):

@@ -186,7 +186,13 @@ typedef struct {
 /* BiquadD::design + Biquad::new (biquad.rs:25-38,83-154): coef = b0,b1,b2,na1,na2.  Host, pure. */
 int sdr_biquad_design(const sdr_biquad_design_t *d, float rate, float coef[5]);
 
-#define SDR_PLL_FAST_MATH 1u /* f32 device atan2f/sincosf instead of the libm-matching f64 path */
+/* atan2 / sin / cos of the PLL recurrence (pll.rs:72,76).  Default (flags = 0): f32 routines within ~1 ulp of libm's
+ * atan2f / sinf / cosf, arranged for the depth of the dependent chain (231 cycles per sample).  SDR_PLL_F64_MATH: the
+ * same functions evaluated in f64 and rounded to f32 (equal to libm's result for all but ~1e-4 of the arguments), 455
+ * cycles per sample.  Both meet the same parity bars against the CPU oracle.  SDR_PLL_FAST_MATH is
+ * accepted for source compatibility and has no effect (it selected the f32 routines when f64 was the default). */
+#define SDR_PLL_FAST_MATH 1u
+#define SDR_PLL_F64_MATH 2u
 
 typedef struct {
     const sdr_pll_design_t *designs; /* n_designs entries */
@@ -337,7 +343,7 @@ typedef struct {
     size_t n_stations;
     float rate;     /* input sample rate; main.rs:32 uses 1 800 000 */
     float pilot;    /* pilot tone in Hz; 0 selects main.rs:54's 19 000 */
-    unsigned flags; /* SDR_PLL_FAST_MATH */
+    unsigned flags; /* SDR_PLL_F64_MATH */
     int device;
     void *stream;
 } sdr_fm_config_t;

@@ -5,7 +5,7 @@ R=${ROUND_TAG:-r01}
 timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
 tail -15 gpurun_out/pytest_gpu.log
 : > gpurun_out/bench_all.jsonl
-for wl in c2 c1 c1c fir255_u8 c3 c3chain c3chain_fastest c3chain_linear c4 c4fast c4_1024 fm c5_8 c5_9 c5_10 c5_11 c5_12 c5_13 c5_14 c5_15 c5_16; do
+for wl in c2 c1 c1c fir255_u8 c3 c3chain c3chain_fastest c3chain_linear c4 c4f64 c4_1024 fm c5_8 c5_9 c5_10 c5_11 c5_12 c5_13 c5_14 c5_15 c5_16; do
   extra="--no-e2e --no-cpu"
   if [ "$wl" = "c2" ]; then extra=""; fi
   timeout 600 python bench.py --workload $wl --steps 10 --warmup 3 $extra >> gpurun_out/bench_all.jsonl 2>> gpurun_out/bench_all.err

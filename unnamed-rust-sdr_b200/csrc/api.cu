@@ -884,7 +884,7 @@ extern "C" int sdr_pll_process_dev(sdr_pll_t *p, const float *in, size_t n, size
     if (!g.ok) return g.status();
     return pll_launch((const float2 *)in, (long long)n, (long long)in_stride, out, locked, (long long)out_stride,
                       p->d_params, p->n_designs == 1, p->d_state, (int)p->n_streams,
-                      (p->flags & SDR_PLL_FAST_MATH) != 0, p->any_identity, p->stream.s);
+                      (p->flags & SDR_PLL_F64_MATH) == 0, p->any_identity, p->stream.s);
 }
 
 extern "C" int sdr_pll_process(sdr_pll_t *p, const float *in, size_t n, size_t in_stride, float *out, uint8_t *locked,
@@ -906,7 +906,7 @@ extern "C" int sdr_pll_process(sdr_pll_t *p, const float *in, size_t n, size_t i
     if (rc) return rc;
     rc = pll_launch((const float2 *)p->d_in.p, (long long)n, (long long)n, (float *)p->d_out.p, (uint8_t *)p->d_lk.p,
                     (long long)n, p->d_params, p->n_designs == 1, p->d_state, (int)S,
-                    (p->flags & SDR_PLL_FAST_MATH) != 0, p->any_identity, st);
+                    (p->flags & SDR_PLL_F64_MATH) == 0, p->any_identity, st);
     if (rc) return rc;
     rc = copy2d(out, out_stride * 4, p->d_out.p, n * 4, n * 4, S, cudaMemcpyDeviceToHost, st);
     if (!rc) rc = copy2d(locked, out_stride, p->d_lk.p, n, n, S, cudaMemcpyDeviceToHost, st);
@@ -924,7 +924,7 @@ extern "C" int sdr_pll_stereo_decode_dev(sdr_pll_t *p, const float *v, size_t n,
     DeviceGuard g(p->dev);
     if (!g.ok) return g.status();
     return pll_stereo_launch(v, (long long)n, (long long)in_stride, out_md, (long long)out_stride, p->d_params,
-                             p->n_designs == 1, p->d_state, (int)p->n_streams, (p->flags & SDR_PLL_FAST_MATH) != 0,
+                             p->n_designs == 1, p->d_state, (int)p->n_streams, (p->flags & SDR_PLL_F64_MATH) == 0,
                              p->stream.s);
 }
 
@@ -945,7 +945,7 @@ extern "C" int sdr_pll_stereo_decode(sdr_pll_t *p, const float *v, size_t n, siz
     rc = copy2d(p->d_in.p, n * 4, v, in_stride * 4, n * 4, S, cudaMemcpyHostToDevice, st);
     if (rc) return rc;
     rc = pll_stereo_launch((const float *)p->d_in.p, (long long)n, (long long)n, (float *)p->d_out.p, (long long)n,
-                           p->d_params, p->n_designs == 1, p->d_state, (int)S, (p->flags & SDR_PLL_FAST_MATH) != 0, st);
+                           p->d_params, p->n_designs == 1, p->d_state, (int)S, (p->flags & SDR_PLL_F64_MATH) == 0, st);
     if (rc) return rc;
     rc = copy2d(out_md, out_stride * 8, p->d_out.p, n * 8, n * 8, S, cudaMemcpyDeviceToHost, st);
     if (rc) return rc;

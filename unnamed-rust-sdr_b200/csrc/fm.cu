@@ -92,7 +92,7 @@ extern "C" sdr_fm_t *sdr_fm_create(const sdr_fm_config_t *cfg, int *err) {
     dd.loopfilter = {SDR_BQ_LOWPASS, 80000.0f, 0.7f};
     dd.outputfilter = {SDR_BQ_IDENTITY, 0.f, 0.f};
     dd.lockfilter = {SDR_BQ_LOWPASS, 20000.0f, 0.7f};
-    sdr_pll_config_t pc = {&dd, 1, f->n_st, f->rate, cfg->flags & SDR_PLL_FAST_MATH, f->dev, st};
+    sdr_pll_config_t pc = {&dd, 1, f->n_st, f->rate, cfg->flags & (SDR_PLL_FAST_MATH | SDR_PLL_F64_MATH), f->dev, st};
     f->demod = sdr_pll_create(&pc, &rc);
     if (!f->demod) { *err = rc; fm_free(f); return nullptr; }
 
@@ -101,7 +101,7 @@ extern "C" sdr_fm_t *sdr_fm_create(const sdr_fm_config_t *cfg, int *err) {
     pd.loopfilter = {SDR_BQ_LOWPASS, 200.0f, 0.7f};
     pd.outputfilter = {SDR_BQ_LOWPASS, 20.0f, 0.7f};
     pd.lockfilter = {SDR_BQ_LOWPASS, 20.0f, 0.7f};
-    sdr_pll_config_t pp = {&pd, 1, f->n_st, f->rate_mid, cfg->flags & SDR_PLL_FAST_MATH, f->dev, st};
+    sdr_pll_config_t pp = {&pd, 1, f->n_st, f->rate_mid, cfg->flags & (SDR_PLL_FAST_MATH | SDR_PLL_F64_MATH), f->dev, st};
     f->pilot = sdr_pll_create(&pp, &rc);
     if (!f->pilot) { *err = rc; fm_free(f); return nullptr; }
 

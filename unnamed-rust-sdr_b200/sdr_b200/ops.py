@@ -318,7 +318,7 @@ class PllDesign:
 class PllBatch:
     """n_streams independent filter::Pll instances (pll.rs:13-85)."""
 
-    def __init__(self, designs, n_streams, rate, fast_math=False, device=0, stream=None, _handle=None):
+    def __init__(self, designs, n_streams, rate, fast_math=True, device=0, stream=None, _handle=None):
         self.n_streams = int(n_streams)
         if _handle is not None:
             self.h = _handle
@@ -326,7 +326,7 @@ class PllBatch:
         arr = (F.PllDesign * len(designs))(*[d._c() for d in designs])
         self._arr = arr
         cfg = F.PllConfig(C.cast(arr, C.c_void_p), len(designs), self.n_streams, rate,
-                          F.PLL_FAST_MATH if fast_math else 0, device, _stream_ptr(stream))
+                          0 if fast_math else F.PLL_F64_MATH, device, _stream_ptr(stream))
         self._cfg = cfg
         err = C.c_int(0)
         self.h = lib().sdr_pll_create(C.byref(cfg), C.byref(err))
@@ -441,9 +441,9 @@ class FmStereo:
     u8 IQ -> Pll demodulator -> /75000 -> SincFastest to 144 kHz -> pilot Pll + (mono, diff) -> SincBest to 48 kHz ->
     Lr de-emphasis -> (left, right)."""
 
-    def __init__(self, n_stations=1, rate=1.8e6, pilot=0.0, fast_math=False, device=0, stream=None):
+    def __init__(self, n_stations=1, rate=1.8e6, pilot=0.0, fast_math=True, device=0, stream=None):
         self.n_stations = int(n_stations)
-        cfg = F.FmConfig(self.n_stations, rate, pilot, F.PLL_FAST_MATH if fast_math else 0, device, _stream_ptr(stream))
+        cfg = F.FmConfig(self.n_stations, rate, pilot, 0 if fast_math else F.PLL_F64_MATH, device, _stream_ptr(stream))
         err = C.c_int(0)
         self.h = lib().sdr_fm_create(C.byref(cfg), C.byref(err))
         if not self.h:
@@ -489,7 +489,7 @@ class FmStereo:
 class Channelizer:
     """n_channels x (Fir<f32,Complex<f32>> -> Pll): BASELINE config 4."""
 
-    def __init__(self, taps, design, n_channels, rate, input_format="c64", fast_math=False, strict=False,
+    def __init__(self, taps, design, n_channels, rate, input_format="c64", fast_math=True, strict=False,
                  device=0, stream=None):
         taps = np.ascontiguousarray(taps, np.float32)
         self._taps = taps
@@ -499,7 +499,7 @@ class Channelizer:
                          F.FIR_STRICT_ORDER if strict else 0, device, _stream_ptr(stream))
         arr = (F.PllDesign * 1)(design._c())
         self._arr = arr
-        pc = F.PllConfig(C.cast(arr, C.c_void_p), 1, self.n_channels, rate, F.PLL_FAST_MATH if fast_math else 0,
+        pc = F.PllConfig(C.cast(arr, C.c_void_p), 1, self.n_channels, rate, 0 if fast_math else F.PLL_F64_MATH,
                          device, None)
         err = C.c_int(0)
         self.h = lib().sdr_channelizer_create(C.byref(fc), C.byref(pc), C.byref(err))
