@@ -7,9 +7,11 @@
 // Every f32 operation is issued in the reference's order with explicit _rn intrinsics so the
 // compiler cannot contract mul+add into FMA (rustc never does).  The three transcendental calls
 // (atan2, cos, sin) are the only place where results can differ from the host libm:
-//   default   : evaluated in f64 (own branch-free routines, ~1e-12) and rounded to f32: differs from a correctly
-//               rounded libm only at rare near-ties
-//   FAST_MATH : the same routines in f32 (1-2 ulp)
+//   default          : own branch-free f32 routines within ~1 ulp of libm's atan2f / sinf / cosf, arranged for the depth
+//                      and the instruction count of the dependent chain (231 cycles per sample)
+//   SDR_PLL_F64_MATH : evaluated in f64 (~1e-12) and rounded to f32: differs from a correctly rounded libm only at rare
+//                      near-ties (455 cycles per sample)
+// Both track the CPU oracle to the same bars (tests/test_gpu_pll_resample.py).
 // Data movement: a warp moves [32 streams x 32 samples] tiles between HBM and shared memory with
 // 256-byte row segments, so the lane-per-stream inner loop reads shared memory, not strided HBM.
 #include "kernels.h"
@@ -41,28 +43,11 @@ __device__ __forceinline__ float bq_apply(const Biquad1 &c, float v, float &x1, 
     return out;
 }
 
-// ---- branch-free atan2 / sincos, evaluated in T = double (default: the f32 results are the correctly rounded ones
-// except for ~1e-4 of the arguments, like the f64 libm calls they replace) or T = float (FAST_MATH: 1-2 ulp) ----------
-// The PLL is one dependent chain per stream, so what matters is the DEPTH of these routines, not their instruction
-// count: no slow-path branches, one reciprocal, Estrin-evaluated polynomials.
-template <typename T> __device__ __forceinline__ T fma_t(T a, T b, T c);
-template <> __device__ __forceinline__ float fma_t<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }
-template <> __device__ __forceinline__ double fma_t<double>(double a, double b, double c) { return __fma_rn(a, b, c); }
-
-// num / den for finite den != 0, |num| <= |den| up to a factor 2: f32 reciprocal seed + Newton steps in T (error ~2^-46
-// in double, ~1 ulp in float).  Branch-free: operands far from 1 are first rescaled by 2^+-64 (exact) so that the seed
-// neither overflows nor flushes -- a NaN here would poison the loop state for good.
-template <typename T>
-__device__ __forceinline__ T div_t(T num, T den) {
-    const float ad = fabsf((float)den);
-    const T sc = ad < 5.4210109e-20f ? T(1.8446744073709552e19) : (ad > 1.8446744e19f ? T(5.421010862427522e-20) : T(1.0));
-    num *= sc;
-    den *= sc;
-    T r = (T)__frcp_rn((float)den);
-    if (sizeof(T) == 8) r = fma_t(r, fma_t(-den, r, T(1.0)), r);
-    const T q = num * r;
-    return fma_t(fma_t(-den, q, num), r, q);
-}
+// ---- branch-free atan2 / sincos -------------------------------------------------------------------------------------
+// Two sets: f32 routines within ~1 ulp (default) and, with SDR_PLL_F64_MATH, f64 evaluation rounded to f32 (the f32
+// results are then the correctly rounded ones except for ~1e-4 of the arguments, like the f64 libm calls they replace).
+// The PLL is one dependent chain per stream on a single warp, so what matters is the DEPTH of these routines and their
+// instruction count: no slow-path branches, one reciprocal, Estrin-evaluated polynomials.
 
 // f64 quotient for the atan2 below, 0 < den < 1e300 (f32 magnitudes widened to f64: no rescaling needed): the
 // 20-bit hardware seed (MUFU.RCP64H, no f32 round trip) and ONE Newton step give 2^-40 -- the result is rounded to f32
@@ -73,41 +58,6 @@ __device__ __forceinline__ double div_fast64(double num, double den) {
     const double e = __fma_rn(-den, r0, 1.0);
     const double r1 = __fma_rn(r0, e, r0);
     return num * r1;
-}
-
-// atan(t) = t + t * z * A(z), z = t^2 <= tan^2(pi/8): Taylor coefficients (-1)^k / (2k+1), NT terms, Estrin
-template <typename T, int NT>
-__device__ __forceinline__ T atan_poly(T z) {
-    // a[i] = (-1)^(i+1) / (2i + 3)
-    T a[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] = (i < NT) ? ((i & 1) ? T(1.0) : T(-1.0)) / T(2 * i + 3) : T(0.0);
-    const T z2 = z * z, z4 = z2 * z2, z8 = z4 * z4;
-    T p[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) p[i] = fma_t(a[2 * i + 1], z, a[2 * i]);
-    T q[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) q[i] = fma_t(p[2 * i + 1], z2, p[2 * i]);
-    const T r0 = fma_t(q[1], z4, q[0]), r1 = fma_t(q[3], z4, q[2]);
-    return z * fma_t(r1, z8, r0);
-}
-
-template <typename T>
-__device__ __forceinline__ T atan2_generic(float yf, float xf) {
-    const T x = (T)xf, y = (T)yf;
-    const T ax = fabs(x), ay = fabs(y);
-    const T mx = fmax(ax, ay), mn = fmin(ax, ay);
-    const bool red = mn > T(0.41421356237309503) * mx;  // tan(pi/8): atan(t) = pi/4 + atan((t-1)/(t+1))
-    const T num = red ? mn - mx : mn;
-    const T den = red ? mn + mx : mx;
-    const T t = (den == T(0.0)) ? T(0.0) : div_t(num, den);
-    const T pz = atan_poly<T, sizeof(T) == 8 ? 14 : 9>(t * t);
-    T r = fma_t(t, pz, t);
-    r = red ? T(0.78539816339744831) + r : r;
-    r = (ay > ax) ? T(1.5707963267948966) - r : r;
-    r = (__float_as_int(xf) < 0) ? T(3.1415926535897932) - r : r;  // sign bit, so that atan2(+-0, -0) = +-pi
-    return (__float_as_int(yf) < 0) ? -r : r;
 }
 
 // The f64 routine on the PLL's dependent chain, arranged for DEPTH (a dependent DFMA costs ~18 cycles here):
@@ -145,60 +95,21 @@ __device__ __forceinline__ double atan2_f64(float yf, float xf) {
     return __fma_rn(S, r, C);
 }
 
-template <typename T>
-__device__ __forceinline__ T atan2_t(float yf, float xf) {
-    if constexpr (sizeof(T) == 8) return atan2_f64(yf, xf);
-    else return atan2_generic<T>(yf, xf);
-}
-
-// sin and cos of an f32 argument |x| < ~100 (here |x| < 2 pi): Cody-Waite reduction by pi/2, Taylor polynomials on
-// [-pi/4, pi/4] (degree 13 / 14 in double, 9 / 10 in float)
-template <typename T>
-__device__ __forceinline__ void sincos_t(float xf, T &sn, T &cs) {
+// sin and cos of an f32 argument |x| < ~100 (here |x| < 2 pi) in f64: one-constant reduction by pi/2 (|k| <= 64: the dropped
+// 6e-17 * k is far below the 1e-10 the f32 result needs), 4-term near-minimax polynomials in 2 Estrin levels (sin: relative
+// error 1.9e-11, cos: absolute 1.9e-10 on |r| <= pi/4)
+__device__ __forceinline__ void sincos_f64(float xf, double &sn, double &cs) {
     const float kf = rintf(xf * 0.63661977236758134f);
     const int q = (int)kf;
-    const T k = (T)kf;
-    if constexpr (sizeof(T) == 8) {
-        // depth-first f64 variant: one-constant reduction (|k| <= 64: the dropped 6e-17 * k is far below the 1e-10 the
-        // f32 result needs), 4-term near-minimax polynomials in 2 Estrin levels (sin: relative error 1.9e-11,
-        // cos: absolute 1.9e-10 on |r| <= pi/4)
-        const double r = __fma_rn(-k, 1.5707963267948966, (double)xf);
-        const double s = r * r, s2 = s * s, rs = r * s;
-        const double S = __fma_rn(__fma_rn(2.7249925803001736e-06, s, -0.00019840086735384028), s2,
-                                  __fma_rn(0.0083333318747102047, s, -0.1666666666385529));
-        const double Cc = __fma_rn(__fma_rn(2.4463788293291526e-05, s, -0.001388758915560089), s2,
-                                   __fma_rn(0.041666650644517043, s, -0.49999999969119313));
-        const double sr = __fma_rn(rs, S, r), cr = __fma_rn(s, Cc, 1.0);
-        const double a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
-        sn = (q & 2) ? -a : a;
-        cs = ((q + 1) & 2) ? -b : b;
-        return;
-    }
-    T r;
-    if (sizeof(T) == 8) {
-        r = fma_t(-k, T(1.5707963267948966), (T)xf);
-        r = fma_t(-k, T(6.123233995736766e-17), r);
-    } else {
-        r = fma_t(-k, T(1.5703125), (T)xf);
-        r = fma_t(-k, T(4.837512969970703125e-4), r);
-        r = fma_t(-k, T(7.549789948768648e-8), r);
-    }
-    const T s = r * r, s2 = s * s, s4 = s2 * s2;
-    // sin r = r + r s (S0 + S1 s + ... ), cos r = 1 + s (C0 + C1 s + ...)
-    const T S0 = T(-1.0 / 6), S1 = T(1.0 / 120), S2 = T(-1.0 / 5040), S3 = T(1.0 / 362880), S4 = T(-1.0 / 39916800),
-            S5 = T(1.0 / 6227020800.0);
-    const T C0 = T(-0.5), C1 = T(1.0 / 24), C2 = T(-1.0 / 720), C3 = T(1.0 / 40320), C4 = T(-1.0 / 3628800),
-            C5 = T(1.0 / 479001600), C6 = T(-1.0 / 87178291200.0);
-    T ps, pc;
-    if (sizeof(T) == 8) {
-        ps = fma_t(fma_t(S5, s, S4), s4, fma_t(fma_t(S3, s, S2), s2, fma_t(S1, s, S0)));
-        pc = fma_t(fma_t(C6, s2, fma_t(C5, s, C4)), s4, fma_t(fma_t(C3, s, C2), s2, fma_t(C1, s, C0)));
-    } else {
-        ps = fma_t(S4, s4, fma_t(fma_t(S3, s, S2), s2, fma_t(S1, s, S0)));
-        pc = fma_t(C4, s4, fma_t(fma_t(C3, s, C2), s2, fma_t(C1, s, C0)));
-    }
-    const T sr = fma_t(r * s, ps, r), cr = fma_t(s, pc, T(1.0));
-    const T a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;   // quadrant
+    const double k = (double)kf;
+    const double r = __fma_rn(-k, 1.5707963267948966, (double)xf);
+    const double s = r * r, s2 = s * s, rs = r * s;
+    const double S = __fma_rn(__fma_rn(2.7249925803001736e-06, s, -0.00019840086735384028), s2,
+                              __fma_rn(0.0083333318747102047, s, -0.1666666666385529));
+    const double Cc = __fma_rn(__fma_rn(2.4463788293291526e-05, s, -0.001388758915560089), s2,
+                               __fma_rn(0.041666650644517043, s, -0.49999999969119313));
+    const double sr = __fma_rn(rs, S, r), cr = __fma_rn(s, Cc, 1.0);
+    const double a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
     sn = (q & 2) ? -a : a;
     cs = ((q + 1) & 2) ? -b : b;
 }
@@ -279,7 +190,7 @@ __device__ __forceinline__ float2 pll_step(const PllParams &p, const Biquad1 &lf
     const float lr = bq_apply<GEN>(lf, cr, s.lx1r, s.lx2r, s.ly1r, s.ly2r);
     const float li = bq_apply<GEN>(lf, ci, s.lx1i, s.lx2i, s.ly1i, s.ly2i);
     // phasedif = arg * gain                   (pll.rs:72)
-    const float arg = FAST ? atan2_fast(li, lr) : (float)atan2_t<double>(li, lr);
+    const float arg = FAST ? atan2_fast(li, lr) : (float)atan2_f64(li, lr);
     const float phasedif = __fmul_rn(arg, p.gain);
     // nphase += reference + phasedif; nphase = nphase.fract()      (pll.rs:73-74)
     float nph = __fadd_rn(s.nphase, __fadd_rn(p.reference, phasedif));
@@ -309,7 +220,7 @@ __device__ __forceinline__ float2 pll_step(const PllParams &p, const Biquad1 &lf
         s.vim = sn;
     } else {
         double sn, cs;
-        sincos_t<double>(phase, sn, cs);
+        sincos_f64(phase, sn, cs);
         s.vre = (float)cs;
         s.vim = (float)sn;
     }
