@@ -175,6 +175,7 @@ __host__ __device__ constexpr size_t um_smem_bytes(int R, int PC, int KS, bool d
 // is ~100 instructions on the per-tile path of every role.
 __device__ __forceinline__ void split_work(long long w, int ntiles, int n_ch, int &ch, long long &tile) {
     if (n_ch == 1) { ch = 0; tile = w; }
+    else if (w <= 0x7fffffffLL) { const unsigned c = (unsigned)w / (unsigned)ntiles; ch = (int)c; tile = (long long)((unsigned)w - c * (unsigned)ntiles); }
     else { ch = (int)(w / ntiles); tile = w - (long long)ch * ntiles; }
 }
 
