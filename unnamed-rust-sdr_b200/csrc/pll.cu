@@ -8,7 +8,7 @@
 // compiler cannot contract mul+add into FMA (rustc never does).  The three transcendental calls
 // (atan2, cos, sin) are the only place where results can differ from the host libm:
 //   default          : own branch-free f32 routines within ~1 ulp of libm's atan2f / sinf / cosf, arranged for the depth
-//                      and the instruction count of the dependent chain (231 cycles per sample)
+//                      and the instruction count of the dependent chain (222 cycles per sample)
 //   SDR_PLL_F64_MATH : evaluated in f64 (~1e-12) and rounded to f32: differs from a correctly rounded libm only at rare
 //                      near-ties (455 cycles per sample)
 // Both track the CPU oracle to the same bars (tests/test_gpu_pll_resample.py).
@@ -120,10 +120,10 @@ __device__ __forceinline__ void sincos_f64(float xf, double &sn, double &cs) {
 // resulting trajectories to the same bars as the f64 routines above (measured: max 3.2e-6 / median 2.0e-7 of full
 // scale against 3.6e-6 / 1.4e-7 -- a last-bit difference in arg or in the NCO is far below one ulp of the f32 phase
 // accumulator it is added to).
-//   atan2: |y|, |x| ordered by two FMNMX; BOTH quotients mn / mx and (mn - mx) / (mn + mx) (the tan(pi/8) reduction) are
-//          formed -- MUFU.RCP + one Newton step each -- so that the select between them waits for nothing; atan(t) =
-//          t + t z A(z), z = t^2 <= tan^2(pi/8), A of degree 4 (near-minimax, relative error 2.8e-9), Estrin in 3 levels;
-//          the octant fix-ups are one fma(S, r, C), S = +-1 and C from the operand signs, off the chain.
+//   atan2: |y|, |x| ordered by two FMNMX; t = mn / mx by MUFU.RCP + one Newton step; atan(t) = t + t z A(z), z = t^2 in
+//          [0, 1], A of degree 8 (near-minimax), Estrin; the octant fix-ups are one fma(S, r, C), S = +-1 and C from the
+//          operand signs, off the chain.  Against f64 atan2 on 2e6 random arguments (numpy model of the same operations,
+//          rcp.approx perturbed by +-1 ulp): mean 0.37 ulp, 0.5 % of the results beyond 1 ulp, max 1.8.
 //   sincos: k = rint(x * 2/pi) by the 1.5 * 2^23 magic number (no FRND / F2I on the chain), two-constant Cody-Waite,
 //          degree-3 near-minimax polynomials in s = r^2 for (sin r / r - 1) / s and (cos r - 1) / s (errors 7e-11,
 //          3.4e-10), Estrin in 2 levels, quadrant from the low bits of the biased float, sign by XOR.
@@ -140,24 +140,25 @@ __device__ __forceinline__ float div_nr(float num, float den) {  // den in [2^-1
 __device__ __forceinline__ float atan2_fast(float yf, float xf) {
     const float axf = fabsf(xf), ayf = fabsf(yf);
     const float mx = fmaxf(axf, ayf), mn = fminf(axf, ayf);
-    const bool red = mn > 0.41421357f * mx;
     const bool swap = ayf > axf, xneg = __float_as_int(xf) < 0, yneg = __float_as_int(yf) < 0;
-    float C = red ? 0.78539816339744831f : 0.0f, S = 1.0f;
-    if (swap) { C = 1.5707963267948966f - C; S = -S; }
+    float C = 0.0f, S = 1.0f;
+    if (swap) { C = 1.5707963267948966f; S = -S; }
     if (xneg) { C = 3.1415926535897932f - C; S = -S; }
     if (yneg) { C = -C; S = -S; }
-    // ONE division behind the select (the main warp is issue bound at ~2 cycles per instruction: a second speculative
-    // quotient costs more than the select's latency).  No range branch: the divisor is clamped from below (0 / 0 -> 0, as
-    // atan2(+-0, +-0) needs); magnitudes beyond 2^126, where rcp.approx.ftz flushes to zero, are not supported by this
-    // routine (the products of pll.rs:71 overflow there anyway), NaN propagates as it does in the reference.
-    const float num = red ? mn - mx : mn;
-    const float den = fmaxf(red ? mn + mx : mx, 1e-37f);
-    const float t = div_nr(num, den);
-    const float z = t * t, z2 = z * z, tz = t * z;
-    const float p0 = __fmaf_rn(0.199996680021286f, z, -0.3333333432674408f);
-    const float p1 = __fmaf_rn(0.10767315328121185f, z, -0.14266839623451233f);
-    const float q = __fmaf_rn(-0.06515224277973175f, z2, p1);
-    const float A = __fmaf_rn(q, z2, p0);
+    // t = mn / mx in [0, 1]: the reciprocal is issued straight behind the FMNMX (a tan(pi/8) reduction would put a
+    // compare and two selects in front of it -- measured: 2 operations more on the chain for one polynomial level
+    // less).  No range branch: the divisor is clamped from below (0 / 0 -> 0, as atan2(+-0, +-0) needs); magnitudes beyond
+    // 2^126, where rcp.approx.ftz flushes to zero, are not supported by this routine (the products of pll.rs:71 overflow
+    // there anyway), NaN propagates as it does in the reference.
+    const float t = div_nr(mn, fmaxf(mx, 1e-37f));
+    // atan(t) = t + t z A(z), z = t^2 in [0, 1], A of degree 8 (near-minimax, relative error of atan 1.5e-8), Estrin
+    const float z = t * t, z2 = z * z, z4 = z2 * z2, z8 = z4 * z4, tz = t * z;
+    const float p01 = __fmaf_rn(0.19999796152114868f, z, -0.3333333134651184f);
+    const float p23 = __fmaf_rn(0.11042594909667969f, z, -0.14279702305793762f);
+    const float p45 = __fmaf_rn(0.06321871280670166f, z, -0.08690944314002991f);
+    const float p67 = __fmaf_rn(0.014019518159329891f, z, -0.03671013563871384f);
+    const float q0 = __fmaf_rn(p23, z2, p01), q1 = __fmaf_rn(p67, z2, p45);
+    const float A = __fmaf_rn(-0.0025140501093119383f, z8, __fmaf_rn(q1, z4, q0));
     const float r = __fmaf_rn(tz, A, t);
     return __fmaf_rn(S, r, C);
 }
