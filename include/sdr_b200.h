@@ -187,7 +187,7 @@ typedef struct {
 int sdr_biquad_design(const sdr_biquad_design_t *d, float rate, float coef[5]);
 
 /* atan2 / sin / cos of the PLL recurrence (pll.rs:72,76).  Default (flags = 0): f32 routines within ~1 ulp of libm's
- * atan2f / sinf / cosf, arranged for the depth of the dependent chain (222 cycles per sample).  SDR_PLL_F64_MATH: the
+ * atan2f / sinf / cosf, arranged for the depth of the dependent chain (219 cycles per sample).  SDR_PLL_F64_MATH: the
  * same functions evaluated in f64 and rounded to f32 (equal to libm's result for all but ~1e-4 of the arguments), 455
  * cycles per sample.  Both meet the same parity bars against the CPU oracle.  SDR_PLL_FAST_MATH is
  * accepted for source compatibility and has no effect (it selected the f32 routines when f64 was the default). */

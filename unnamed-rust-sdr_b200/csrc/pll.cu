@@ -8,7 +8,7 @@
 // compiler cannot contract mul+add into FMA (rustc never does).  The three transcendental calls
 // (atan2, cos, sin) are the only place where results can differ from the host libm:
 //   default          : own branch-free f32 routines within ~1 ulp of libm's atan2f / sinf / cosf, arranged for the depth
-//                      and the instruction count of the dependent chain (222 cycles per sample)
+//                      and the instruction count of the dependent chain (219 cycles per sample)
 //   SDR_PLL_F64_MATH : evaluated in f64 (~1e-12) and rounded to f32: differs from a correctly rounded libm only at rare
 //                      near-ties (455 cycles per sample)
 // Both track the CPU oracle to the same bars (tests/test_gpu_pll_resample.py).
@@ -162,8 +162,11 @@ __device__ __forceinline__ float atan2_fast(float yf, float xf) {
     const float r = __fmaf_rn(tz, A, t);
     return __fmaf_rn(S, r, C);
 }
-__device__ __forceinline__ void sincos_fast(float xf, float &sn, float &cs) {
-    const float kb = __fmaf_rn(xf, 0.63661977236758134f, 12582912.0f);
+// xf = fl(2 pi f) with f = the fractional phase in (-1, 1): the quadrant k = rint(4 f) is taken from f, beside the
+// multiplication that forms xf (one operation less on the chain than rint(xf * 2/pi); the two agree except within an ulp of
+// a quadrant boundary, where either k leaves |r| <= pi/4 + 1e-6)
+__device__ __forceinline__ void sincos_fast(float xf, float f, float &sn, float &cs) {
+    const float kb = __fmaf_rn(f, 4.0f, 12582912.0f);
     const float kf = kb - 12582912.0f;
     const int q = __float_as_int(kb);  // low two bits = k mod 4
     float r = __fmaf_rn(-kf, 1.57079637050628662109375f, xf);
@@ -216,7 +219,7 @@ __device__ __forceinline__ float2 pll_step(const PllParams &p, const Biquad1 &lf
     s.nphase = nph;
     if (FAST) {
         float sn, cs;
-        sincos_fast(phase, sn, cs);
+        sincos_fast(phase, nph, sn, cs);
         s.vre = cs;
         s.vim = sn;
     } else {
