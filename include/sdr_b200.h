@@ -193,6 +193,10 @@ int sdr_biquad_design(const sdr_biquad_design_t *d, float rate, float coef[5]);
  * accepted for source compatibility and has no effect (it selected the f32 routines when f64 was the default). */
 #define SDR_PLL_FAST_MATH 1u
 #define SDR_PLL_F64_MATH 2u
+/* always run the general kernel (per-sample filter-kind tests, fract for any step size) instead of the one specialised
+ * for designs without Identity sub-filters and with |reference / rate| + pi |gain| < 1.  Same results bit for bit where
+ * both apply (tests/test_gpu_pll_resample.py); for testing. */
+#define SDR_PLL_GENERAL_KERNEL 4u
 
 typedef struct {
     const sdr_pll_design_t *designs; /* n_designs entries */

@@ -148,6 +148,35 @@ def test_pll_agrees_to_phase_ulps_away_from_the_atan2_branch_cut(sdr, fast):
     assert d.max() <= 1e-6 and np.array_equal(lk[:first], sl[:first])
 
 
+@pytest.mark.parametrize("fast", [True, False])
+def test_pll_general_and_specialised_kernels_agree_bit_for_bit(sdr, fast):
+    """The kernel specialised for designs without Identity sub-filters and with a step per sample below one cycle drops
+    the per-sample kind tests and the general trunc of f32::fract; where both apply the two must give the same bits
+    (SDR_PLL_GENERAL_KERNEL forces the general one).  A design OUTSIDE the specialised kernel's range (|reference| / rate
+    + pi * gain > 1) is checked against the oracle over the prefix before its first approach to the atan2 branch cut."""
+    import pyref
+    _, v = O.freq_sweep(1800000.0, 20000.0, True, -200000.0, 200000.0)
+    x = np.stack([np.roll(v, 7 * s) for s in range(5)]).astype(np.complex64)
+    a, la = sdr.PllBatch([example_design(sdr)], 5, 1.8e6, fast_math=fast).process(x)
+    b, lb = sdr.PllBatch([example_design(sdr)], 5, 1.8e6, fast_math=fast, general=True).process(x)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and np.array_equal(la, lb)
+    # wide step: reference 0.494 cycles per sample, gain 0.18 -> |reference| / rate + pi * gain = 1.06: the general kernel,
+    # with nphase wrapping through +-1 every other sample; loop filter at 400 kHz keeps this loop well damped (the
+    # restatement shows |arg| <= 0.88 rad over the whole signal: nowhere near the cut)
+    rate, ref, gain, lbw = 1.8e6, 890000.0, 0.18, 400000.0
+    B = sdr.BiquadD
+    d_gpu = sdr.PllDesign(ref, gain, B.LowPass(lbw, 0.7), B.LowPass(20000.0, 0.7), B.LowPass(20000.0, 0.7))
+    d_cpu = O.pll_design(ref, gain, (O.BQ_LOWPASS, lbw, 0.7), (O.BQ_LOWPASS, 20000.0, 0.7), (O.BQ_LOWPASS, 20000.0, 0.7))
+    k = np.arange(1200)
+    xs = np.exp(1j * (2 * np.pi * (ref + 300.0) * k / rate + 0.2 * np.sin(2 * np.pi * 1e3 * k / rate))).astype(np.complex64)
+    ro, rl = O.Pll(d_cpu, rate).apply(xs)
+    _, _, arg = pyref.pll_trace(ref, gain, (lbw, 0.7), (20000.0, 0.7), (20000.0, 0.7), rate, xs)
+    assert np.abs(arg).max() < np.pi - 0.25
+    out, lk = sdr.PllBatch([d_gpu], 1, rate, fast_math=fast).process(xs)
+    d = np.abs(out.astype(np.float64) - ro) / (rate * gain * np.pi)
+    assert d.max() <= 1e-5 and np.array_equal(lk, rl), float(d.max())
+
+
 @pytest.mark.parametrize("n_ch,n", [(128, 8192), (1024, 2048)])
 def test_channelizer_default_fir_at_c4_channel_counts(sdr, n_ch, n):
     """C4 as bench.py runs it: the DEFAULT (non-strict) multi-channel FIR feeding the PLLs, at the per-GPU (128) and

@@ -837,6 +837,7 @@ extern "C" sdr_pll_t *sdr_pll_create(const sdr_pll_config_t *cfg, int *err) {
         // the specialised kernel also assumes |nphase + reference + gain * arg| < 2 (nphase in (-1, 1), |arg| <= pi), so
         // that f32::fract needs no general trunc; designs with a larger step per sample take the general kernel
         if (!(std::fabs(q.reference) + 3.1416f * std::fabs(q.gain) < 0.999f)) p->any_identity = true;
+        if (cfg->flags & SDR_PLL_GENERAL_KERNEL) p->any_identity = true;
         int rc = sdr_biquad_design(&d.loopfilter, cfg->rate, q.lc);
         if (!rc) rc = sdr_biquad_design(&d.outputfilter, cfg->rate, q.oc);
         if (!rc) rc = sdr_biquad_design(&d.lockfilter, cfg->rate, q.kc);

@@ -11,6 +11,7 @@ FIR_STRICT_ORDER, FIR_NO_TENSOR, FIR_NO_TCGEN05, FIR_PLANAR, FIR_SPLIT2 = 1, 2, 
 FFT_SHIFT, FFT_NORM, FFT_RFFT = 1, 2, 4
 PLL_FAST_MATH = 1
 PLL_F64_MATH = 2
+PLL_GENERAL_KERNEL = 4
 BQ_IDENTITY, BQ_LOWPASS, BQ_HIGHPASS, BQ_BANDPASS, BQ_NOTCH, BQ_LR = range(6)
 SRC_SINC_BEST_QUALITY, SRC_SINC_MEDIUM_QUALITY, SRC_SINC_FASTEST, SRC_ZERO_ORDER_HOLD, SRC_LINEAR = range(5)
 

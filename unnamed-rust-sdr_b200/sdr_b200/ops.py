@@ -318,7 +318,7 @@ class PllDesign:
 class PllBatch:
     """n_streams independent filter::Pll instances (pll.rs:13-85)."""
 
-    def __init__(self, designs, n_streams, rate, fast_math=True, device=0, stream=None, _handle=None):
+    def __init__(self, designs, n_streams, rate, fast_math=True, device=0, stream=None, _handle=None, general=False):
         self.n_streams = int(n_streams)
         if _handle is not None:
             self.h = _handle
@@ -326,7 +326,8 @@ class PllBatch:
         arr = (F.PllDesign * len(designs))(*[d._c() for d in designs])
         self._arr = arr
         cfg = F.PllConfig(C.cast(arr, C.c_void_p), len(designs), self.n_streams, rate,
-                          0 if fast_math else F.PLL_F64_MATH, device, _stream_ptr(stream))
+                          (0 if fast_math else F.PLL_F64_MATH) | (F.PLL_GENERAL_KERNEL if general else 0), device,
+                          _stream_ptr(stream))
         self._cfg = cfg
         err = C.c_int(0)
         self.h = lib().sdr_pll_create(C.byref(cfg), C.byref(err))
