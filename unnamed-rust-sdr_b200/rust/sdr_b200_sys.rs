@@ -15,6 +15,8 @@ pub const SDR_FIR_STRICT_ORDER: c_uint = 1;
 pub const SDR_FFT_SHIFT: c_uint = 1;
 pub const SDR_FFT_NORM: c_uint = 2;
 pub const SDR_FFT_RFFT: c_uint = 4;
+/// sdr_pll_config_t.flags: atan2 / sin / cos evaluated in f64 and rounded to f32 (default: f32 routines within ~1 ulp)
+pub const SDR_PLL_F64_MATH: c_uint = 2;
 
 pub enum sdr_fir_t {}
 pub enum sdr_fft_t {}
